@@ -1,0 +1,258 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+Test infrastructure only: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never imported by pitchvis_b200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("sr", C.c_float),
+        ("n_fft", C.c_uint64),
+        ("min_freq", C.c_float),
+        ("octaves", C.c_uint32),
+        ("buckets_per_octave", C.c_uint32),
+        ("sparsity_quantile", C.c_float),
+        ("quality", C.c_float),
+        ("gamma", C.c_float),
+    ]
+
+
+class OrcError(C.Structure):
+    _fields_ = [("code", C.c_int), ("a", C.c_float), ("b", C.c_float), ("n", C.c_uint64)]
+
+
+class OrcFilterParams(C.Structure):
+    _fields_ = [
+        ("freq", C.c_float),
+        ("window_length", C.c_float),
+        ("sr_downscaling_factor", C.c_uint64),
+        ("minimum_needed_window_size", C.c_uint64),
+    ]
+
+
+class OrcCsr(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32),
+        ("cols", C.c_int32),
+        ("nnz", C.c_int64),
+        ("indptr", C.POINTER(C.c_int32)),
+        ("indices", C.POINTER(C.c_int32)),
+        ("data", C.POINTER(C.c_float)),
+    ]
+
+
+class OrcGroup(C.Structure):
+    _fields_ = [
+        ("window_begin", C.c_uint64),
+        ("window_end", C.c_uint64),
+        ("filter_bank", OrcCsr),
+        ("negative_filter_bank", OrcCsr),
+    ]
+
+
+ORC_OK, ORC_ABOVE_NYQUIST, ORC_WINDOW_EXCEEDS_NFFT, ORC_ASSERT, ORC_BAD_LENGTH = range(5)
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so if missing or stale (gcc, a few seconds)."""
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    stale = not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    fp = C.POINTER(C.c_float)
+    L.orc_default_params.argtypes = [C.POINTER(OrcParams)]
+    L.orc_default_params.restype = None
+    L.orc_filter_bank_params.argtypes = [C.POINTER(OrcParams), C.POINTER(OrcFilterParams), C.POINTER(OrcError)]
+    L.orc_vqt_new.argtypes = [C.POINTER(OrcParams), C.POINTER(C.c_void_p), C.POINTER(OrcError)]
+    L.orc_vqt_free.argtypes = [C.c_void_p]
+    L.orc_vqt_free.restype = None
+    L.orc_n_buckets.argtypes = [C.c_void_p]
+    L.orc_n_buckets.restype = C.c_size_t
+    L.orc_delay_seconds.argtypes = [C.c_void_p]
+    L.orc_delay_seconds.restype = C.c_double
+    L.orc_num_groups.argtypes = [C.c_void_p]
+    L.orc_num_groups.restype = C.c_size_t
+    L.orc_group_at.argtypes = [C.c_void_p, C.c_size_t]
+    L.orc_group_at.restype = C.POINTER(OrcGroup)
+    L.orc_vqt_set_group.argtypes = [
+        C.c_void_p, C.c_size_t, C.c_int, C.c_int32, C.c_int32, C.c_int64,
+        C.POINTER(C.c_int32), C.POINTER(C.c_int32), fp,
+    ]
+    L.orc_calc_instant_db.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_int, fp, fp]
+    L.orc_calc_batch_db.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, fp]
+    L.orc_power_to_db.argtypes = [fp, C.c_size_t, fp]
+    L.orc_power_to_db.restype = None
+    L.orc_test_create_sines.argtypes = [C.POINTER(OrcParams), fp, C.c_size_t, C.c_float, fp]
+    L.orc_test_create_sines.restype = None
+    L.orc_max_threads.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_params() -> OrcParams:
+    p = OrcParams()
+    lib().orc_default_params(C.byref(p))
+    return p
+
+
+def make_params(**kw) -> OrcParams:
+    p = default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def hires_params() -> OrcParams:
+    """SURVEY.md section 8 'hi-res' configuration (config 4)."""
+    return make_params(sr=44100.0, n_fft=65536, min_freq=55.0, octaves=8, buckets_per_octave=168,
+                       quality=0.8, gamma=3.84, sparsity_quantile=0.999)
+
+
+class OracleError(Exception):
+    def __init__(self, err: OrcError):
+        self.code, self.a, self.b, self.n = err.code, err.a, err.b, err.n
+        super().__init__(f"oracle error code={err.code} a={err.a} b={err.b} n={err.n}")
+
+
+@dataclass
+class CsrView:
+    rows: int
+    cols: int
+    indptr: np.ndarray
+    indices: np.ndarray
+    data: np.ndarray  # complex64
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.shape[0])
+
+
+def _csr_view(m: OrcCsr) -> CsrView:
+    nnz = int(m.nnz)
+    indptr = np.ctypeslib.as_array(m.indptr, shape=(m.rows + 1,)).copy()
+    if nnz:
+        indices = np.ctypeslib.as_array(m.indices, shape=(nnz,)).copy()
+        data = np.ctypeslib.as_array(m.data, shape=(2 * nnz,)).copy().view(np.complex64)
+    else:
+        indices = np.zeros(0, np.int32)
+        data = np.zeros(0, np.complex64)
+    return CsrView(int(m.rows), int(m.cols), indptr, indices, data)
+
+
+class OracleVqt:
+    """Mirror of pitchvis_analysis::vqt::Vqt on the CPU oracle."""
+
+    def __init__(self, params: OrcParams | None = None):
+        self.params = params if params is not None else default_params()
+        self._h = C.c_void_p()
+        err = OrcError()
+        rc = lib().orc_vqt_new(C.byref(self.params), C.byref(self._h), C.byref(err))
+        if rc != ORC_OK:
+            raise OracleError(err)
+        self.n_buckets = int(lib().orc_n_buckets(self._h))
+        self.n_fft = int(self.params.n_fft)
+        self.delay = float(lib().orc_delay_seconds(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().orc_vqt_free(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def num_groups(self) -> int:
+        return int(lib().orc_num_groups(self._h))
+
+    def group(self, g: int):
+        grp = lib().orc_group_at(self._h, g).contents
+        return (int(grp.window_begin), int(grp.window_end)), _csr_view(grp.filter_bank), _csr_view(
+            grp.negative_filter_bank)
+
+    def set_group(self, g: int, neg: bool, rows, cols, indptr, indices, data_c64):
+        indptr = np.ascontiguousarray(indptr, np.int32)
+        indices = np.ascontiguousarray(indices, np.int32)
+        data = np.ascontiguousarray(data_c64, np.complex64).view(np.float32)
+        rc = lib().orc_vqt_set_group(
+            self._h, g, int(neg), rows, cols, indices.shape[0],
+            indptr.ctypes.data_as(C.POINTER(C.c_int32)), indices.ctypes.data_as(C.POINTER(C.c_int32)),
+            _fptr(data))
+        assert rc == ORC_OK
+
+    def calculate_vqt_instant_in_db(self, x: np.ndarray, mode: int = 0, return_power: bool = False):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(self.n_buckets, np.float32)
+        pw = np.empty(self.n_buckets, np.float32)
+        rc = lib().orc_calc_instant_db(self._h, _fptr(x), x.shape[0], mode, _fptr(out), _fptr(pw))
+        if rc == ORC_BAD_LENGTH:
+            raise ValueError("input must be exactly n_fft samples")
+        assert rc == ORC_OK
+        return (out, pw) if return_power else out
+
+    def calculate_batch_db(self, audio: np.ndarray, hop: int, n_frames: int | None = None, mode: int = 0,
+                           n_threads: int = 0) -> np.ndarray:
+        audio = np.ascontiguousarray(audio, np.float32)
+        if n_frames is None:
+            n_frames = (audio.shape[0] - self.n_fft) // hop + 1 if audio.shape[0] >= self.n_fft else 0
+        out = np.empty((n_frames, self.n_buckets), np.float32)
+        rc = lib().orc_calc_batch_db(self._h, _fptr(audio), audio.shape[0], hop, n_frames, mode, n_threads,
+                                     _fptr(out))
+        if rc == ORC_BAD_LENGTH:
+            raise ValueError("audio too short for the requested frames")
+        assert rc == ORC_OK
+        return out
+
+
+def filter_bank_params(params: OrcParams):
+    nb = params.octaves * params.buckets_per_octave
+    arr = (OrcFilterParams * nb)()
+    err = OrcError()
+    rc = lib().orc_filter_bank_params(C.byref(params), arr, C.byref(err))
+    if rc != ORC_OK:
+        raise OracleError(err)
+    return arr
+
+
+def power_to_db(power: np.ndarray) -> np.ndarray:
+    power = np.ascontiguousarray(power, np.float32)
+    out = np.empty_like(power)
+    lib().orc_power_to_db(_fptr(power), power.shape[0], _fptr(out))
+    return out
+
+
+def test_create_sines(params: OrcParams, freqs, t_diff: float = 0.0) -> np.ndarray:
+    f = np.ascontiguousarray(freqs, np.float32)
+    wave = np.empty(int(params.n_fft), np.float32)
+    lib().orc_test_create_sines(C.byref(params), _fptr(f), f.shape[0], t_diff, _fptr(wave))
+    return wave
+
+
+test_create_sines.__test__ = False  # not a pytest test
