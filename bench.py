@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- VQT frames/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload chords60|hires60]
+
+A "step" is one pass of the hot path over one batch of synthetic audio.  At N=1 the workload is
+BASELINE.json configs[1]: 60 s of synthetic polyphonic audio (random chords), default VqtParameters,
+hop 368 -> 3507 frames.  With N ranks (torchrun, one rank per GPU) every rank transforms its own
+60 s recording (weak scaling, independent streams, no collective on the data path).
+
+  value        frames/s, device-timed (CUDA events per step), audio already resident in HBM
+  e2e          frames/s through the host-buffer C-ABI entry (pvqt_calc_batch_db): H2D + kernels + D2H
+  roofline     K-fft (the dominant kernel): algorithmic bytes / measured launch duration vs measured HBM peak
+  cpu_baseline the CPU oracle (a C port of the reference algorithm, f32, OpenMP) on the host cores
+
+`--impl reference` times that CPU port alone (the Rust reference cannot be built in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "vqt_frames_per_sec"
+UNIT = "frames/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload(name: str, seed: int):
+    from pitchvis_b200 import synth
+    import pitchvis_b200 as pv
+    if name == "chords60":
+        params = pv.VqtParameters.default()
+        audio = synth.polyphonic_chords(60.0, params.sr, seed=seed)
+        hop = synth.HOP_DEFAULT
+    elif name == "hires60":
+        params = pv.VqtParameters.hires()
+        audio = synth.polyphonic_chords(60.0, params.sr, seed=seed)
+        hop = synth.HOP_HIRES
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    n_frames = synth.frames_in(audio.shape[0], params.n_fft, hop)
+    return params, audio, hop, n_frames
+
+
+def oracle_params(name: str):
+    import orc
+    return orc.default_params() if name == "chords60" else orc.hires_params()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank: int, world: int):
+    """CPU arm: the oracle's reference-faithful f32 path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    import orc
+    params, audio, hop, n_frames = workload(args.workload, seed=0)
+    v = orc.OracleVqt(oracle_params(args.workload))
+    threads = orc.lib().orc_max_threads()
+    for _ in range(args.warmup):
+        v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+    dt = time.perf_counter() - t0
+    fps = args.steps * n_frames / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: 60 s synthetic polyphonic audio, hop {hop}, {n_frames} frames/step"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} passes over all {n_frames} frames of the workload, "
+                                   "oracle f32 path (C port of vqt.rs:866-954; the Rust crate cannot be built here)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, audio, hop, n_frames):
+    import orc
+    v = orc.OracleVqt(oracle_params(args.workload))
+    threads = orc.lib().orc_max_threads()
+    v.calculate_batch_db(audio, hop, min(n_frames, 256), mode=1, n_threads=threads)  # warm caches / plans
+    t0 = time.perf_counter()
+    v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+    one = time.perf_counter() - t0
+    reps = max(1, min(200, int(12.0 * threads / max(one * threads, 1e-3))))  # ~12 s of CPU work in total
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    n1 = min(n_frames, 1024)
+    v.calculate_batch_db(audio, hop, n1, mode=1, n_threads=1)
+    dt1 = time.perf_counter() - t1
+    return {"value": reps * n_frames / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{reps} passes over all {n_frames} frames (oracle f32 path, OpenMP, {threads} threads)",
+            "single_thread_value": n1 / dt1, "single_thread_ms_per_frame": 1e3 * dt1 / n1,
+            "reference_published_ms_per_frame": 0.091}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="chords60", choices=["chords60", "hires60"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    import pitchvis_b200 as pv
+    from pitchvis_b200 import _ffi
+    lib = _ffi.load()
+
+    params, audio, hop, n_frames = workload(args.workload, seed=rank)
+    vqt = pv.Vqt(params, device=local_rank)
+    nb = vqt.n_buckets
+    h = vqt.handle
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError(_ffi.last_error())
+
+    # ---- device-resident arm ----------------------------------------------------------------
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_out = pv.DeviceBuffer(vqt, n_frames * nb * 4)
+    d_audio.upload(audio)
+    flush_bytes = 512 << 20   # > 126 MB L2: evicts audio, spectra scratch and output between steps
+    d_flush = pv.DeviceBuffer(vqt, flush_bytes)
+    ev = [C.c_void_p() for _ in range(2 * args.steps)]
+    for e in ev:
+        chk(lib.pvqt_event_create(h, C.byref(e)))
+
+    def step():
+        pv.calc_db_device(vqt, d_audio, 1, 0, hop, n_frames, d_out)
+
+    def flush():
+        chk(lib.pvqt_dev_memset(h, d_flush.ptr, 0, flush_bytes))
+
+    for _ in range(args.warmup):
+        flush(); step()
+    pv.synchronize(vqt)
+    launches0 = vqt.launch_count
+
+    def barrier():
+        pv.synchronize(vqt)
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush()
+        chk(lib.pvqt_event_record(h, ev[2 * i]))
+        step()
+        chk(lib.pvqt_event_record(h, ev[2 * i + 1]))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = vqt.launch_count - launches0
+    step_ms = []
+    for i in range(args.steps):
+        ms = C.c_float()
+        chk(lib.pvqt_event_elapsed_ms(h, ev[2 * i], ev[2 * i + 1], C.byref(ms)))
+        step_ms.append(ms.value)
+    dev_ms_total = float(sum(step_ms))
+
+    # ---- per-kernel durations (same steps, event pairs around each launch) ---------------------
+    chk(lib.pvqt_set_profiling(h, 1))
+    for _ in range(args.steps):
+        flush(); step()
+    fft_ms, spmm_ms = C.c_double(), C.c_double()
+    fft_n, spmm_n = C.c_uint64(), C.c_uint64()
+    chk(lib.pvqt_get_profile(h, 1, C.byref(fft_ms), C.byref(fft_n), C.byref(spmm_ms), C.byref(spmm_n)))
+    chk(lib.pvqt_set_profiling(h, 0))
+
+    # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------
+    pin_in, pin_out = C.c_void_p(), C.c_void_p()
+    chk(lib.pvqt_host_alloc_pinned(audio.nbytes, C.byref(pin_in)))
+    chk(lib.pvqt_host_alloc_pinned(n_frames * nb * 4, C.byref(pin_out)))
+    C.memmove(pin_in, audio.ctypes.data, audio.nbytes)
+    fp = C.POINTER(C.c_float)
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        flush()
+        chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
+    pv.synchronize(vqt)
+    e2e_s = time.perf_counter() - t0
+    result_checksum = float(np.ctypeslib.as_array(C.cast(pin_out, fp), shape=(n_frames * nb,)).sum())
+
+    # ---- reduce over ranks: max time, total frames -------------------------------------------
+    dev_ms_max, e2e_s_max = dev_ms_total, e2e_s
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+
+    total_frames = world * n_frames
+    value = total_frames * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = total_frames * e2e_steps / e2e_s_max
+
+    if rank == 0:
+        first = int(lib.pvqt_first_sample_used(h))
+        union = params.n_fft - first
+        bytes_per_frame = 4 * union + 4 * nb                      # 35,120 B at the defaults
+        fft_avg_ms = fft_ms.value / max(1, fft_n.value)
+        frames_per_launch = n_frames * args.steps / max(1, fft_n.value)
+        peak, peak_src = measured_peak_gbs()
+        achieved = bytes_per_frame * frames_per_launch / (fft_avg_ms * 1e-3) / 1e9
+        whole = bytes_per_frame * n_frames / (statistics.median(step_ms) * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: 60 s synthetic polyphonic audio per GPU (random chords, seed = rank), "
+                            f"default hop {hop}, {n_frames} frames/step/GPU (BASELINE.json configs[1])",
+                "n_fft": params.n_fft, "n_buckets": nb, "hop": hop, "frames_per_step_per_gpu": n_frames,
+                "l2": f"flushed between timed steps ({flush_bytes >> 20} MiB memset)",
+                "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes),
+                    "d2h_bytes_per_step": int(n_frames * nb * 4), "steps": e2e_steps,
+                    "api": "pvqt_calc_batch_db (pinned host buffers in and out)", "checksum": result_checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "fft_groups_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": bytes_per_frame, "frames_per_launch": frames_per_launch,
+                "kernel_avg_ms": fft_avg_ms, "kernel_share_of_step": fft_ms.value / max(1e-9, fft_ms.value + spmm_ms.value),
+                "spmm_db_avg_ms": spmm_ms.value / max(1, spmm_n.value),
+                "whole_step_achieved": whole, "whole_step_frac": whole / peak,
+                "note": "the path is FP32/shared-memory bound (SURVEY.md 8d); HBM fraction reported as BASELINE asks",
+            },
+            "step_ms": {"median": statistics.median(step_ms), "min": min(step_ms), "max": max(step_ms)},
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, audio, hop, n_frames)
+        elif not args.no_cpu_baseline:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": "measured at N=1 only"}
+        print(json.dumps(line), flush=True)
+
+    for e in ev:
+        lib.pvqt_event_destroy(h, e)
+    lib.pvqt_host_free_pinned(pin_in)
+    lib.pvqt_host_free_pinned(pin_out)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,915 @@
+// pvqt_api.cu -- C-ABI layer of libpvqt.so (include/pvqt.h): handle management, the
+// device-side plan (twiddles, banded kernel layout), launch orchestration, host<->device
+// staging and the single-process multi-GPU dispatcher.
+//
+// There is no CPU compute path in this library: every calc entry point runs the sm_100a
+// kernels of vqt_kernels.cu or fails with PVQT_CUDA_ERROR.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernel_builder.hpp"
+#include "pvqt.h"
+#include "vqt_device.cuh"
+
+using namespace pvqt_dev;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(pvqt_status st, const std::string &msg)
+{
+    g_last_error = msg;
+    return st;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return PVQT_CUDA_ERROR;
+}
+
+#define PVQT_CUDA(call)                                             \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);         \
+    } while (0)
+
+constexpr double kPi = 3.14159265358979323846;
+
+// mirrors plan_radix() of vqt_kernels.cu (host copy used to size the twiddle tables)
+int host_plan_radix(int nc, int pass)
+{
+    static const int plans[][5] = {
+        {32, 16, 2, 1, 1},    {64, 16, 4, 1, 1},     {128, 16, 8, 1, 1},    {256, 16, 16, 1, 1},
+        {512, 16, 8, 4, 1},   {1024, 16, 16, 4, 1},  {2048, 16, 16, 8, 1},  {4096, 16, 16, 16, 1},
+        {8192, 16, 16, 8, 4}, {16384, 16, 16, 16, 4},
+    };
+    for (const auto &p : plans)
+        if (p[0] == nc) return pass < 4 ? p[1 + pass] : 1;
+    return 1;
+}
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want)
+    {
+        if (want <= bytes) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace
+
+struct pvqt {
+    pvqt_params params{};
+    pvqt_host::Kernel kernel;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // device plan
+    std::vector<void *> owned;          // device allocations freed on destroy
+    FftParams fft{};                    // template (frames/spec filled per launch)
+    SpmmParams spmm{};
+    int fft_block_threads = 256;
+    int spmm_frames_per_cta = 8;
+    std::vector<uint32_t> col_lo, n_cols, spec_off;
+    size_t first_sample_used = 0;
+    size_t last_sample_used = 0;        // one past
+    uint32_t chunk_frames = 8192;
+
+    // scratch
+    DeviceBuffer spec, d_audio, d_out;
+    std::atomic<uint64_t> launches{0};
+
+    // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
+    bool profiling = false;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;
+};
+
+struct pvqt_kernel {
+    pvqt_host::Kernel kernel;
+};
+
+namespace {
+
+template <typename T>
+cudaError_t upload(pvqt *v, const std::vector<T> &host, const T **dev)
+{
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    v->owned.push_back(p);
+    if (!host.empty()) {
+        e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
+    *dev = static_cast<const T *>(p);
+    return cudaSuccess;
+}
+
+int build_device_plan(pvqt *v)
+{
+    const auto &groups = v->kernel.window_groups;
+    if (groups.empty() || groups.size() > (size_t)kMaxGroups)
+        return fail(PVQT_UNSUPPORTED, "unsupported number of window groups: " + std::to_string(groups.size()));
+
+    int max_threads_per_fft = 0;
+    v->first_sample_used = v->params.n_fft;
+    v->last_sample_used = 0;
+    for (const auto &g : groups) {
+        const uint64_t n = g.window_size();
+        if (n < 64 || n > 32768 || (n & (n - 1)) != 0)
+            return fail(PVQT_UNSUPPORTED, "window group of " + std::to_string(n) +
+                                              " samples: the sm_100a FFT plans cover powers of two in [64, 32768]");
+        max_threads_per_fft = std::max<int>(max_threads_per_fft, (int)(n / 2 / kPointsPerThread));
+        v->first_sample_used = std::min<size_t>(v->first_sample_used, g.window_begin);
+        v->last_sample_used = std::max<size_t>(v->last_sample_used, g.window_end);
+    }
+    v->fft_block_threads = max_threads_per_fft <= 256 ? 256 : (max_threads_per_fft <= 512 ? 512 : 1024);
+
+    // ---- FFT descriptors -------------------------------------------------------------
+    FftParams &F = v->fft;
+    std::memset(&F, 0, sizeof(F));
+    F.n_groups = (int)groups.size();
+    int spec_cursor = 0;
+    v->col_lo.clear(); v->n_cols.clear(); v->spec_off.clear();
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const auto &g = groups[gi];
+        const int nc = (int)(g.window_size() / 2);
+        int lo = nc, hi = 0;
+        for (const pvqt_host::Csr *m : {&g.filter_bank, &g.negative_filter_bank})
+            for (int32_t c : m->indices) { lo = std::min(lo, c); hi = std::max(hi, c); }
+        if (hi < lo) { lo = 0; hi = 0; }  // group without coefficients: keep one (unused) column
+        FftGroup &d = F.group[gi];
+        d.window_begin = (int32_t)g.window_begin;
+        d.log2_nc = 0;
+        while ((1 << d.log2_nc) < nc) ++d.log2_nc;
+        d.col_lo = lo;
+        d.col_hi = hi;
+        d.spec_offset = spec_cursor;
+        d.frames_per_cta = v->fft_block_threads / (nc / kPointsPerThread);
+        spec_cursor += hi - lo + 1;
+        v->col_lo.push_back(lo); v->n_cols.push_back(hi - lo + 1); v->spec_off.push_back(d.spec_offset);
+
+        int ns = 1;
+        for (int pass = 0; pass < kMaxFftPasses; ++pass) {
+            const int r = host_plan_radix(nc, pass);
+            if (r == 1) break;
+            if (pass > 0) {
+                std::vector<float2> tw((size_t)(r - 1) * ns);
+                for (int rr = 1; rr < r; ++rr)
+                    for (int k = 0; k < ns; ++k) {
+                        const double a = -2.0 * kPi * (double)rr * (double)k / ((double)ns * r);
+                        tw[(size_t)(rr - 1) * ns + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+                    }
+                cudaError_t e = upload(v, tw, &d.twiddle[pass]);
+                if (e != cudaSuccess) return cuda_fail(e, "upload twiddles");
+            }
+            ns *= r;
+        }
+        std::vector<float2> st((size_t)(hi - lo + 1));
+        for (int c = lo; c <= hi; ++c) {
+            const double a = -2.0 * kPi * (double)c / (double)(2 * nc);
+            st[c - lo] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        cudaError_t e = upload(v, st, &d.split_twiddle);
+        if (e != cudaSuccess) return cuda_fail(e, "upload split twiddles");
+    }
+    F.spec_stride = (spec_cursor + 1) & ~1;  // even: frame rows stay 16-byte aligned
+
+    // ---- banded sliced-ELL layout of the spectral kernel ------------------------------
+    const int nb = (int)v->kernel.n_buckets;
+    const int n_blocks = (nb + kSpmmRowsPerBlock - 1) / kSpmmRowsPerBlock;
+    struct RowBand { int col0 = 0, len = 0, ncol0 = 0, nlen = 0; const pvqt_host::Csr *m = nullptr, *mn = nullptr; int local = 0; int spec = 0; int lo = 0; };
+    std::vector<RowBand> rows((size_t)n_blocks * kSpmmRowsPerBlock);
+    {
+        int row = 0;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const auto &g = groups[gi];
+            for (int r = 0; r < g.filter_bank.rows; ++r, ++row) {
+                RowBand &b = rows[row];
+                b.m = &g.filter_bank; b.mn = &g.negative_filter_bank; b.local = r;
+                b.spec = F.group[gi].spec_offset; b.lo = F.group[gi].col_lo;
+                const int s = g.filter_bank.indptr[r], e = g.filter_bank.indptr[r + 1];
+                if (e > s) {
+                    b.col0 = g.filter_bank.indices[s];
+                    b.len = g.filter_bank.indices[e - 1] - b.col0 + 1;
+                }
+                if (g.negative_filter_bank.nnz() > 0) {
+                    const int ns_ = g.negative_filter_bank.indptr[r], ne = g.negative_filter_bank.indptr[r + 1];
+                    if (ne > ns_) {
+                        b.ncol0 = g.negative_filter_bank.indices[ns_];
+                        b.nlen = g.negative_filter_bank.indices[ne - 1] - b.ncol0 + 1;
+                    }
+                }
+            }
+        }
+        if (row != nb) return fail(PVQT_PANIC, "kernel rows do not add up to n_buckets");
+    }
+    std::vector<SpmmBlock> blocks(n_blocks);
+    std::vector<int2> row_cols(rows.size(), make_int2(0, 0));
+    std::vector<float2> values;
+    for (int b = 0; b < n_blocks; ++b) {
+        int w = 0, nw = 0;
+        for (int l = 0; l < kSpmmRowsPerBlock; ++l) {
+            w = std::max(w, rows[(size_t)b * kSpmmRowsPerBlock + l].len);
+            nw = std::max(nw, rows[(size_t)b * kSpmmRowsPerBlock + l].nlen);
+        }
+        blocks[b].val_base = (int)(values.size() / kSpmmRowsPerBlock);
+        blocks[b].width = w;
+        values.resize(values.size() + (size_t)w * kSpmmRowsPerBlock, make_float2(0.f, 0.f));
+        blocks[b].nval_base = (int)(values.size() / kSpmmRowsPerBlock);
+        blocks[b].nwidth = nw;
+        values.resize(values.size() + (size_t)nw * kSpmmRowsPerBlock, make_float2(0.f, 0.f));
+        for (int l = 0; l < kSpmmRowsPerBlock; ++l) {
+            const size_t ri = (size_t)b * kSpmmRowsPerBlock + l;
+            const RowBand &rb = rows[ri];
+            if (!rb.m) continue;
+            // rows without a (conjugate) band still run the block's loop over zero coefficients:
+            // point them at a valid column
+            row_cols[ri] = make_int2(rb.len > 0 ? rb.spec + (rb.col0 - rb.lo) : rb.spec,
+                                     rb.nlen > 0 ? rb.spec + (rb.ncol0 - rb.lo) : rb.spec);
+            for (int e = rb.m->indptr[rb.local]; e < rb.m->indptr[rb.local + 1]; ++e) {
+                const int j = rb.m->indices[e] - rb.col0;
+                values[((size_t)blocks[b].val_base + j) * kSpmmRowsPerBlock + l] =
+                    make_float2(rb.m->data[e].real(), rb.m->data[e].imag());
+            }
+            if (rb.nlen > 0)
+                for (int e = rb.mn->indptr[rb.local]; e < rb.mn->indptr[rb.local + 1]; ++e) {
+                    const int j = rb.mn->indices[e] - rb.ncol0;
+                    // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg)
+                    values[((size_t)blocks[b].nval_base + j) * kSpmmRowsPerBlock + l] =
+                        make_float2(rb.mn->data[e].real(), -rb.mn->data[e].imag());
+                }
+        }
+    }
+    SpmmParams &S = v->spmm;
+    std::memset(&S, 0, sizeof(S));
+    cudaError_t e;
+    if ((e = upload(v, blocks, &S.blocks)) != cudaSuccess) return cuda_fail(e, "upload blocks");
+    if ((e = upload(v, row_cols, &S.row_cols)) != cudaSuccess) return cuda_fail(e, "upload row_cols");
+    if ((e = upload(v, values, &S.values)) != cudaSuccess) return cuda_fail(e, "upload values");
+    S.n_blocks = n_blocks;
+    S.n_buckets = nb;
+    S.spec_stride = F.spec_stride;
+    S.ref_db = 10.0f * std::log10(0.3f * 0.3f);  // vqt.rs:923,927
+
+    if ((e = configure_kernels(F.spec_stride, nb, &v->spmm_frames_per_cta)) != cudaSuccess)
+        return cuda_fail(e, "configure kernels (is this an sm_100a device?)");
+    return PVQT_OK;
+}
+
+void prof_begin(pvqt *v, int kind, cudaStream_t stream)
+{
+    if (!v->profiling) return;
+    pvqt::Timed t{};
+    t.kind = kind;
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+    cudaEventRecord(t.a, stream);
+    v->timed.push_back(t);
+}
+
+void prof_end(pvqt *v, cudaStream_t stream)
+{
+    if (!v->profiling || v->timed.empty()) return;
+    cudaEventRecord(v->timed.back().b, stream);
+}
+
+// Launch FFT + SpMM/dB for `n_frames` frames laid out as `layout` describes.
+int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
+               size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream)
+{
+    const size_t total = n_streams * frames_per_stream;
+    if (total == 0) return PVQT_OK;
+    if (frames_per_stream > 0xffffffffull) return fail(PVQT_INVALID_ARGUMENT, "frames_per_stream too large");
+    const size_t nb = v->kernel.n_buckets;
+    const uint32_t chunk = v->chunk_frames;
+    if (!d_spec_out) {
+        cudaError_t e = v->spec.reserve((size_t)std::min<size_t>(total, chunk) * v->fft.spec_stride * sizeof(float2));
+        if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
+    }
+    for (size_t f0 = 0; f0 < total; f0 += chunk) {
+        const uint32_t n = (uint32_t)std::min<size_t>(chunk, total - f0);
+        FftParams fp = v->fft;
+        fp.frames.audio = d_audio;
+        fp.frames.stream_stride = stream_stride;
+        fp.frames.hop = hop;
+        fp.frames.frames_per_stream = (uint32_t)frames_per_stream;
+        fp.frames.n_frames = n;
+        fp.frames.first_frame = f0;
+        fp.spec = d_spec_out ? reinterpret_cast<float2 *>(d_spec_out) + f0 * fp.spec_stride
+                             : static_cast<float2 *>(v->spec.ptr);
+        int ctas = 0;
+        for (int g = 0; g < fp.n_groups; ++g) {
+            fp.group[g].cta_begin = ctas;
+            ctas += (int)((n + fp.group[g].frames_per_cta - 1) / fp.group[g].frames_per_cta);
+        }
+        prof_begin(v, 0, stream);
+        cudaError_t e = launch_fft(fp, ctas, v->fft_block_threads, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch fft_groups_kernel");
+        prof_end(v, stream);
+        v->launches.fetch_add(1);
+        if (d_spec_out) continue;
+
+        SpmmParams sp = v->spmm;
+        sp.n_frames = n;
+        sp.spec = fp.spec;
+        sp.out_db = d_out + f0 * nb;
+        sp.out_power = d_power ? d_power + f0 * nb : nullptr;
+        prof_begin(v, 1, stream);
+        e = launch_spmm_db(sp, v->spmm_frames_per_cta, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_kernel");
+        prof_end(v, stream);
+        v->launches.fetch_add(1);
+    }
+    return PVQT_OK;
+}
+
+// Host buffers in/out.  Streams are processed in segments whose audio fits the staging budget;
+// a stream longer than the budget is cut into frame ranges (halo of n_fft - hop samples).
+int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples, size_t hop,
+             size_t frames_per_stream, float *out)
+{
+    const size_t n_fft = v->params.n_fft, nb = v->kernel.n_buckets;
+    if (n_streams == 0 || frames_per_stream == 0) return PVQT_OK;
+    if (!audio || !out) return fail(PVQT_INVALID_ARGUMENT, "null buffer");
+    if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
+    if (n_samples < n_fft || (frames_per_stream - 1) * hop + n_fft > n_samples)
+        return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
+    if (n_streams > 1 && stream_stride < n_samples)
+        return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
+    PVQT_CUDA(cudaSetDevice(v->device));
+
+    const size_t budget = (size_t)128 << 20;  // samples per staged segment (512 MiB)
+    const size_t span = (frames_per_stream - 1) * hop + n_fft;  // samples one stream needs
+    if (span <= budget) {
+        const size_t per_seg = std::max<size_t>(1, budget / span);
+        const size_t dstride = (span + 3) & ~(size_t)3;
+        for (size_t s0 = 0; s0 < n_streams; s0 += per_seg) {
+            const size_t ns = std::min(per_seg, n_streams - s0);
+            PVQT_CUDA(v->d_audio.reserve(ns * dstride * sizeof(float)));
+            PVQT_CUDA(v->d_out.reserve(ns * frames_per_stream * nb * sizeof(float)));
+            PVQT_CUDA(cudaMemcpy2DAsync(v->d_audio.ptr, dstride * sizeof(float), audio + s0 * stream_stride,
+                                        stream_stride * sizeof(float), span * sizeof(float), ns,
+                                        cudaMemcpyHostToDevice, v->stream));
+            int rc = run_device(v, static_cast<const float *>(v->d_audio.ptr), ns, dstride, hop, frames_per_stream,
+                                static_cast<float *>(v->d_out.ptr), nullptr, nullptr, v->stream);
+            if (rc) return rc;
+            PVQT_CUDA(cudaMemcpyAsync(out + s0 * frames_per_stream * nb, v->d_out.ptr,
+                                      ns * frames_per_stream * nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+            PVQT_CUDA(cudaStreamSynchronize(v->stream));
+        }
+    } else {
+        const size_t frames_per_seg = std::max<size_t>(1, (budget - n_fft) / hop + 1);
+        for (size_t s = 0; s < n_streams; ++s) {
+            for (size_t f0 = 0; f0 < frames_per_stream; f0 += frames_per_seg) {
+                const size_t nf = std::min(frames_per_seg, frames_per_stream - f0);
+                const size_t seg_samples = (nf - 1) * hop + n_fft;
+                PVQT_CUDA(v->d_audio.reserve(seg_samples * sizeof(float)));
+                PVQT_CUDA(v->d_out.reserve(nf * nb * sizeof(float)));
+                PVQT_CUDA(cudaMemcpyAsync(v->d_audio.ptr, audio + s * stream_stride + f0 * hop,
+                                          seg_samples * sizeof(float), cudaMemcpyHostToDevice, v->stream));
+                int rc = run_device(v, static_cast<const float *>(v->d_audio.ptr), 1, 0, hop, nf,
+                                    static_cast<float *>(v->d_out.ptr), nullptr, nullptr, v->stream);
+                if (rc) return rc;
+                PVQT_CUDA(cudaMemcpyAsync(out + (s * frames_per_stream + f0) * nb, v->d_out.ptr,
+                                          nf * nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+                PVQT_CUDA(cudaStreamSynchronize(v->stream));
+            }
+        }
+    }
+    return PVQT_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int pvqt_abi_version(void) { return PVQT_ABI_VERSION; }
+
+const char *pvqt_last_error_string(void) { return g_last_error.c_str(); }
+
+int pvqt_device_count(int *count)
+{
+    if (!count) return fail(PVQT_INVALID_ARGUMENT, "count is null");
+    *count = 0;
+    PVQT_CUDA(cudaGetDeviceCount(count));
+    return PVQT_OK;
+}
+
+int pvqt_default_params(pvqt_params *out)
+{
+    if (!out) return fail(PVQT_INVALID_ARGUMENT, "out is null");
+    // vqt.rs:180-214 / Default impl vqt.rs:333-348
+    const float upscale = 1.0f;                // DEFAULT_UPSCALE_FACTOR
+    out->sr = 22050.0f;                        // DEFAULT_SR
+    out->n_fft = 2 * 16384;                    // DEFAULT_N_FFT
+    out->min_freq = 55.0f;                     // DEFAULT_MIN_FREQ
+    out->octaves = 7;                          // DEFAULT_OCTAVES
+    out->buckets_per_octave = 12 * 7 * 1;      // DEFAULT_BUCKETS_PER_OCTAVE
+    out->sparsity_quantile = 0.999f;           // DEFAULT_SPARSITY_QUANTILE
+    out->quality = 1.6f / upscale;             // DEFAULT_Q
+    out->gamma = 4.8f * out->quality;          // DEFAULT_GAMMA
+    return PVQT_OK;
+}
+
+size_t pvqt_params_n_buckets(const pvqt_params *p)
+{
+    return p ? (size_t)p->buckets_per_octave * (size_t)p->octaves : 0;
+}
+
+static void fill_build_error(pvqt_error *err, const pvqt_host::BuildError &be)
+{
+    err->status = be.status;
+    err->highest_frequency = be.highest_frequency;
+    err->nyquist_frequency = be.nyquist_frequency;
+    err->window_length = be.window_length;
+    err->n_fft = be.n_fft;
+}
+
+int pvqt_filter_bank_params(const pvqt_params *params, pvqt_filter_params *out, size_t n, pvqt_error *err)
+{
+    pvqt_error local{};
+    if (!err) err = &local;
+    std::memset(err, 0, sizeof(*err));
+    if (!params || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    std::vector<pvqt_host::FilterParams> fp;
+    pvqt_host::BuildError be;
+    if (!pvqt_host::filter_bank_params(*params, fp, be)) { fill_build_error(err, be); return fail(be.status, be.message); }
+    if (n != fp.size()) return fail(PVQT_BAD_LENGTH, "out must hold n_buckets entries");
+    for (size_t i = 0; i < n; ++i) {
+        out[i].freq = fp[i].freq;
+        out[i].window_length = fp[i].window_length;
+        out[i].sr_downscaling_factor = fp[i].sr_downscaling_factor;
+        out[i].minimum_needed_window_size = fp[i].minimum_needed_window_size;
+    }
+    return PVQT_OK;
+}
+
+int pvqt_kernel_create(const pvqt_params *params, pvqt_kernel **out, pvqt_error *err)
+{
+    pvqt_error local{};
+    if (!err) err = &local;
+    std::memset(err, 0, sizeof(*err));
+    if (!params || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    std::unique_ptr<pvqt_kernel> k(new pvqt_kernel());
+    pvqt_host::BuildError be;
+    if (!pvqt_host::build_kernel(*params, k->kernel, be)) { fill_build_error(err, be); return fail(be.status, be.message); }
+    *out = k.release();
+    return PVQT_OK;
+}
+
+void pvqt_kernel_destroy(pvqt_kernel *k) { delete k; }
+size_t pvqt_kernel_n_buckets(const pvqt_kernel *k) { return k ? k->kernel.n_buckets : 0; }
+double pvqt_kernel_delay_seconds(const pvqt_kernel *k) { return k ? k->kernel.delay_seconds : 0.0; }
+size_t pvqt_kernel_num_window_groups(const pvqt_kernel *k) { return k ? k->kernel.window_groups.size() : 0; }
+
+static int group_window_of(const pvqt_host::Kernel &kernel, size_t group, uint64_t *begin, uint64_t *end)
+{
+    if (group >= kernel.window_groups.size()) return fail(PVQT_INVALID_ARGUMENT, "bad group index");
+    if (begin) *begin = kernel.window_groups[group].window_begin;
+    if (end) *end = kernel.window_groups[group].window_end;
+    return PVQT_OK;
+}
+
+static int group_csr_of(const pvqt_host::Kernel &kernel, size_t group, int negative, pvqt_csr_view *out)
+{
+    if (!out || group >= kernel.window_groups.size()) return fail(PVQT_INVALID_ARGUMENT, "bad group index");
+    const auto &g = kernel.window_groups[group];
+    const pvqt_host::Csr &m = negative ? g.negative_filter_bank : g.filter_bank;
+    out->rows = m.rows;
+    out->cols = m.cols;
+    out->nnz = m.nnz();
+    out->indptr = m.indptr.data();
+    out->indices = m.indices.data();
+    out->data = reinterpret_cast<const float *>(m.data.data());
+    return PVQT_OK;
+}
+
+int pvqt_kernel_group_window(const pvqt_kernel *k, size_t group, uint64_t *begin, uint64_t *end)
+{
+    if (!k) return fail(PVQT_INVALID_ARGUMENT, "null kernel");
+    return group_window_of(k->kernel, group, begin, end);
+}
+
+int pvqt_kernel_group_csr(const pvqt_kernel *k, size_t group, int negative, pvqt_csr_view *out)
+{
+    if (!k) return fail(PVQT_INVALID_ARGUMENT, "null kernel");
+    return group_csr_of(k->kernel, group, negative, out);
+}
+
+int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *err)
+{
+    pvqt_error local{};
+    if (!err) err = &local;
+    std::memset(err, 0, sizeof(*err));
+    if (!params || !out) { err->status = PVQT_INVALID_ARGUMENT; return fail(PVQT_INVALID_ARGUMENT, "null argument"); }
+    *out = nullptr;
+
+    std::unique_ptr<pvqt> v(new pvqt());
+    v->params = *params;
+    pvqt_host::BuildError be;
+    if (!pvqt_host::build_kernel(*params, v->kernel, be)) { fill_build_error(err, be); return fail(be.status, be.message); }
+
+    auto cuda_error = [&](cudaError_t e, const char *what) {
+        err->status = PVQT_CUDA_ERROR;
+        err->cuda_error = (int32_t)e;
+        return cuda_fail(e, what);
+    };
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount (no CPU fallback exists)");
+    if (device < 0 || device >= n_dev) {
+        err->status = PVQT_INVALID_ARGUMENT;
+        return fail(PVQT_INVALID_ARGUMENT, "device " + std::to_string(device) + " out of range (" +
+                                               std::to_string(n_dev) + " CUDA devices)");
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_error(e, "cudaSetDevice");
+    v->device = device;
+    if ((e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return cuda_error(e, "cudaStreamCreate");
+
+    pvqt *raw = v.release();
+    int rc = build_device_plan(raw);
+    if (rc != PVQT_OK) {
+        err->status = rc;
+        std::string keep = g_last_error;
+        pvqt_destroy(raw);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = raw;
+    return PVQT_OK;
+}
+
+void pvqt_destroy(pvqt *v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+    for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (void *p : v->owned) cudaFree(p);
+    v->spec.release();
+    v->d_audio.release();
+    v->d_out.release();
+    delete v;
+}
+
+int pvqt_get_params(const pvqt *v, pvqt_params *out)
+{
+    if (!v || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    *out = v->params;
+    return PVQT_OK;
+}
+size_t pvqt_n_buckets(const pvqt *v) { return v ? v->kernel.n_buckets : 0; }
+size_t pvqt_n_fft(const pvqt *v) { return v ? (size_t)v->params.n_fft : 0; }
+double pvqt_delay_seconds(const pvqt *v) { return v ? v->kernel.delay_seconds : 0.0; }
+size_t pvqt_num_window_groups(const pvqt *v) { return v ? v->kernel.window_groups.size() : 0; }
+int pvqt_device(const pvqt *v) { return v ? v->device : -1; }
+size_t pvqt_first_sample_used(const pvqt *v) { return v ? v->first_sample_used : 0; }
+
+int pvqt_group_window(const pvqt *v, size_t group, uint64_t *begin, uint64_t *end)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    return group_window_of(v->kernel, group, begin, end);
+}
+
+int pvqt_group_csr(const pvqt *v, size_t group, int negative, pvqt_csr_view *out)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    return group_csr_of(v->kernel, group, negative, out);
+}
+
+size_t pvqt_spec_stride(const pvqt *v) { return v ? (size_t)v->fft.spec_stride : 0; }
+
+int pvqt_group_columns(const pvqt *v, size_t group, uint32_t *first_col, uint32_t *n_cols, uint32_t *spec_offset)
+{
+    if (!v || group >= v->col_lo.size()) return fail(PVQT_INVALID_ARGUMENT, "bad group index");
+    if (first_col) *first_col = v->col_lo[group];
+    if (n_cols) *n_cols = v->n_cols[group];
+    if (spec_offset) *spec_offset = v->spec_off[group];
+    return PVQT_OK;
+}
+
+size_t pvqt_frames_in(const pvqt *v, size_t n_samples, size_t hop)
+{
+    if (!v || hop == 0 || n_samples < v->params.n_fft) return 0;
+    return (n_samples - (size_t)v->params.n_fft) / hop + 1;
+}
+
+// ---- compute entry points ------------------------------------------------------------------
+int pvqt_calc_instant_db(pvqt *v, const float *x, size_t n, float *out)
+{
+    if (!v || !x || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    if (n != v->params.n_fft) return fail(PVQT_BAD_LENGTH, "input must be exactly n_fft samples");  // vqt.rs:867-871
+    return run_host(v, x, 1, 0, n, (size_t)v->params.n_fft, 1, out);
+}
+
+int pvqt_calc_batch_db(pvqt *v, const float *audio, size_t n_samples, size_t hop, size_t n_frames, float *out)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    return run_host(v, audio, 1, 0, n_samples, hop, n_frames, out);
+}
+
+int pvqt_calc_frames_db(pvqt *v, const float *frames, size_t n_frames, float *out)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    const size_t n_fft = (size_t)v->params.n_fft;
+    return run_host(v, frames, 1, 0, n_frames * n_fft, n_fft, n_frames, out);
+}
+
+int pvqt_calc_streams_db(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples,
+                         size_t hop, size_t frames_per_stream, float *out)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    return run_host(v, audio, n_streams, stream_stride, n_samples, hop, frames_per_stream, out);
+}
+
+int pvqt_calc_db_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
+                        size_t frames_per_stream, float *d_out, float *d_power, void *cuda_stream)
+{
+    if (!v || !d_audio || !d_out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : v->stream;
+    return run_device(v, d_audio, n_streams, stream_stride, hop, frames_per_stream, d_out, d_power, nullptr, st);
+}
+
+int pvqt_fft_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
+                    size_t frames_per_stream, float *d_spec, void *cuda_stream)
+{
+    if (!v || !d_audio || !d_spec) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : v->stream;
+    return run_device(v, d_audio, n_streams, stream_stride, hop, frames_per_stream, nullptr, nullptr, d_spec, st);
+}
+
+// ---- memory / timing helpers ---------------------------------------------------------------
+int pvqt_dev_alloc(int device, size_t bytes, void **out)
+{
+    if (!out) return fail(PVQT_INVALID_ARGUMENT, "out is null");
+    PVQT_CUDA(cudaSetDevice(device));
+    PVQT_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return PVQT_OK;
+}
+int pvqt_dev_free(int device, void *p)
+{
+    PVQT_CUDA(cudaSetDevice(device));
+    PVQT_CUDA(cudaFree(p));
+    return PVQT_OK;
+}
+int pvqt_host_alloc_pinned(size_t bytes, void **out)
+{
+    if (!out) return fail(PVQT_INVALID_ARGUMENT, "out is null");
+    PVQT_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return PVQT_OK;
+}
+int pvqt_host_free_pinned(void *p)
+{
+    PVQT_CUDA(cudaFreeHost(p));
+    return PVQT_OK;
+}
+int pvqt_memcpy_h2d(pvqt *v, void *dst, const void *src, size_t bytes, int async)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, v->stream));
+    if (!async) PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    return PVQT_OK;
+}
+int pvqt_memcpy_d2h(pvqt *v, void *dst, const void *src, size_t bytes, int async)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, v->stream));
+    if (!async) PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    return PVQT_OK;
+}
+int pvqt_dev_memset(pvqt *v, void *dst, int value, size_t bytes)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaMemsetAsync(dst, value, bytes, v->stream));
+    return PVQT_OK;
+}
+int pvqt_synchronize(pvqt *v)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    return PVQT_OK;
+}
+int pvqt_event_create(pvqt *v, void **out_event)
+{
+    if (!v || !out_event) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    cudaEvent_t ev;
+    PVQT_CUDA(cudaEventCreate(&ev));
+    *out_event = ev;
+    return PVQT_OK;
+}
+int pvqt_event_destroy(pvqt *v, void *event)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+    return PVQT_OK;
+}
+int pvqt_event_record(pvqt *v, void *event)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), v->stream));
+    return PVQT_OK;
+}
+int pvqt_event_elapsed_ms(pvqt *v, void *start, void *stop, float *ms)
+{
+    if (!v || !ms) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(stop)));
+    PVQT_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+    return PVQT_OK;
+}
+uint64_t pvqt_launch_count(const pvqt *v) { return v ? v->launches.load() : 0; }
+
+int pvqt_set_profiling(pvqt *v, int enabled)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    v->profiling = enabled != 0;
+    return PVQT_OK;
+}
+
+int pvqt_get_profile(pvqt *v, int reset, double *fft_ms, uint64_t *fft_launches, double *spmm_ms,
+                     uint64_t *spmm_launches)
+{
+    if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    double ms[2] = {0.0, 0.0};
+    uint64_t n[2] = {0, 0};
+    for (const auto &t : v->timed) {
+        float e = 0.f;
+        PVQT_CUDA(cudaEventSynchronize(t.b));
+        PVQT_CUDA(cudaEventElapsedTime(&e, t.a, t.b));
+        ms[t.kind] += e;
+        n[t.kind] += 1;
+    }
+    if (reset) {
+        for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+        v->timed.clear();
+    }
+    if (fft_ms) *fft_ms = ms[0];
+    if (fft_launches) *fft_launches = n[0];
+    if (spmm_ms) *spmm_ms = ms[1];
+    if (spmm_launches) *spmm_launches = n[1];
+    return PVQT_OK;
+}
+
+// ---- sharding ------------------------------------------------------------------------------
+int pvqt_shard_range(size_t n_units, size_t n_parts, size_t part, size_t *begin, size_t *end)
+{
+    if (n_parts == 0 || part >= n_parts || !begin || !end) return fail(PVQT_INVALID_ARGUMENT, "bad shard request");
+    const size_t base = n_units / n_parts, rem = n_units % n_parts;
+    *begin = part * base + std::min(part, rem);
+    *end = *begin + base + (part < rem ? 1 : 0);
+    return PVQT_OK;
+}
+
+int pvqt_frame_range_samples(size_t n_fft, size_t hop, size_t f0, size_t f1, size_t *s0, size_t *s1)
+{
+    if (!s0 || !s1 || f1 < f0) return fail(PVQT_INVALID_ARGUMENT, "bad frame range");
+    if (f1 == f0) { *s0 = 0; *s1 = 0; return PVQT_OK; }
+    *s0 = f0 * hop;
+    *s1 = (f1 - 1) * hop + n_fft;
+    return PVQT_OK;
+}
+
+}  // extern "C"
+
+// ---- single-process multi-GPU ----------------------------------------------------------------
+struct pvqt_multi {
+    std::vector<pvqt *> handles;
+};
+
+extern "C" {
+
+int pvqt_multi_create(const pvqt_params *params, int n_devices, const int *device_ids, pvqt_multi **out,
+                      pvqt_error *err)
+{
+    if (!out || n_devices <= 0) return fail(PVQT_INVALID_ARGUMENT, "bad multi-device request");
+    *out = nullptr;
+    std::unique_ptr<pvqt_multi> m(new pvqt_multi());
+    for (int i = 0; i < n_devices; ++i) {
+        pvqt *h = nullptr;
+        int rc = pvqt_create(params, device_ids ? device_ids[i] : i, &h, err);
+        if (rc != PVQT_OK) {
+            std::string keep = g_last_error;
+            for (pvqt *p : m->handles) pvqt_destroy(p);
+            g_last_error = keep;
+            return rc;
+        }
+        m->handles.push_back(h);
+    }
+    *out = m.release();
+    return PVQT_OK;
+}
+
+void pvqt_multi_destroy(pvqt_multi *m)
+{
+    if (!m) return;
+    for (pvqt *p : m->handles) pvqt_destroy(p);
+    delete m;
+}
+
+int pvqt_multi_num_devices(const pvqt_multi *m) { return m ? (int)m->handles.size() : 0; }
+pvqt *pvqt_multi_handle(pvqt_multi *m, int index)
+{
+    return (m && index >= 0 && index < (int)m->handles.size()) ? m->handles[index] : nullptr;
+}
+
+}  // extern "C"
+
+namespace {
+
+// run `fn(part)` on one host thread per device; the first non-OK status (and its message) wins
+template <typename Fn>
+int for_each_device(pvqt_multi *m, Fn fn)
+{
+    const size_t n = m->handles.size();
+    std::vector<int> rc(n, PVQT_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> threads;
+    for (size_t i = 0; i < n; ++i)
+        threads.emplace_back([&, i] {
+            rc[i] = fn(i);
+            if (rc[i] != PVQT_OK) msg[i] = g_last_error;
+        });
+    for (auto &t : threads) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rc[i] != PVQT_OK) { g_last_error = msg[i]; return rc[i]; }
+    return PVQT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pvqt_multi_calc_batch_db(pvqt_multi *m, const float *audio, size_t n_samples, size_t hop, size_t n_frames,
+                             float *out)
+{
+    if (!m || m->handles.empty()) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    const size_t n_fft = pvqt_n_fft(m->handles[0]), nb = pvqt_n_buckets(m->handles[0]);
+    if (n_frames == 0) return PVQT_OK;
+    if (n_samples < n_fft || (n_frames - 1) * hop + n_fft > n_samples)
+        return fail(PVQT_BAD_LENGTH, "audio must hold (n_frames - 1) * hop + n_fft samples");
+    return for_each_device(m, [&](size_t i) {
+        size_t f0, f1, s0, s1;
+        pvqt_shard_range(n_frames, m->handles.size(), i, &f0, &f1);
+        if (f1 == f0) return (int)PVQT_OK;
+        pvqt_frame_range_samples(n_fft, hop, f0, f1, &s0, &s1);
+        return pvqt_calc_batch_db(m->handles[i], audio + s0, s1 - s0, hop, f1 - f0, out + f0 * nb);
+    });
+}
+
+int pvqt_multi_calc_streams_db(pvqt_multi *m, const float *audio, size_t n_streams, size_t stream_stride,
+                               size_t n_samples, size_t hop, size_t frames_per_stream, float *out)
+{
+    if (!m || m->handles.empty()) return fail(PVQT_INVALID_ARGUMENT, "null handle");
+    const size_t nb = pvqt_n_buckets(m->handles[0]);
+    return for_each_device(m, [&](size_t i) {
+        size_t s0, s1;
+        pvqt_shard_range(n_streams, m->handles.size(), i, &s0, &s1);
+        if (s1 == s0) return (int)PVQT_OK;
+        return pvqt_calc_streams_db(m->handles[i], audio + s0 * stream_stride, s1 - s0, stream_stride, n_samples, hop,
+                                    frames_per_stream, out + s0 * frames_per_stream * nb);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libpvqt.so, built in-tree (nvcc cross-compiles without a GPU)."""
+    from pitchvis_b200 import build
+    return build.build()
+
+
+@pytest.fixture(scope="session")
+def oracle_default():
+    import orc
+    return orc.OracleVqt()

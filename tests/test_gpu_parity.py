@@ -1,0 +1,261 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerance (BASELINE.json north_star): max |dB_gpu - dB_oracle| <= 1e-3 dB on the power_to_db output,
+and <= 1e-3 dB on the pre-dB power for every bin above -80 dB relative to the frame maximum.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+import pitchvis_b200 as pv
+from pitchvis_b200 import _ffi, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_DB = 1e-3
+HOP = synth.HOP_DEFAULT
+
+
+@pytest.fixture(scope="module")
+def vqt(built_lib):
+    v = pv.Vqt(pv.VqtParameters.default(), device=0)
+    yield v
+    v.close()
+
+
+@pytest.fixture(scope="module")
+def chords():
+    return synth.polyphonic_chords(8.0, 22050.0, seed=0)
+
+
+def _oracle_on_product_kernel(v: pv.Vqt, op) -> orc.OracleVqt:
+    """Oracle runtime on the kernel the product built (what Vqt::kernel() exposes)."""
+    o = orc.OracleVqt(op)
+    for g, wg in enumerate(v.kernel().window_groups):
+        fb = wg.filter_bank
+        o.set_group(g, False, fb.rows, fb.cols, fb.indptr, fb.indices, fb.data)
+        nb = wg.negative_filter_bank
+        if nb is not None:
+            o.set_group(g, True, nb.rows, nb.cols, nb.indptr, nb.indices, nb.data)
+    return o
+
+
+def _power_err_db(p_gpu, p_ref, floor_db=-80.0):
+    """max |10 log10(Pg/Po)| over bins above floor_db relative to each frame's maximum"""
+    p_gpu = np.atleast_2d(p_gpu).astype(np.float64)
+    p_ref = np.atleast_2d(p_ref).astype(np.float64)
+    mask = p_ref >= p_ref.max(axis=1, keepdims=True) * 10 ** (floor_db / 10)
+    mask &= p_ref > 1e-12
+    err = np.abs(10 * np.log10(np.maximum(p_gpu, 1e-300) / np.maximum(p_ref, 1e-300)))
+    return float(err[mask].max()) if mask.any() else 0.0
+
+
+def test_library_is_native(vqt):
+    assert _ffi.load().pvqt_abi_version() == 1
+    assert vqt.n_buckets == 588 and vqt.n_fft == 32768
+    assert int(vqt.delay * 1000) == 98
+
+
+def test_config1_single_frame(vqt, oracle_default):
+    # BASELINE.json configs[0]: 440 Hz + harmonics through the per-frame entry point
+    x = orc.test_create_sines(oracle_default.params, [440, 880, 1320, 1760, 2200])
+    got = vqt.calculate_vqt_instant_in_db(x)
+    ref = oracle_default.calculate_vqt_instant_in_db(x, mode=0)
+    assert got.shape == (588,) and got.dtype == np.float32
+    assert np.abs(got - ref).max() <= TOL_DB
+    single = vqt.calculate_vqt_instant_in_db(orc.test_create_sines(oracle_default.params, [440]))
+    assert int(single.argmax()) == 252 and abs(single.max() - 26.2875) < 5e-3
+
+
+def test_kernel_introspection_matches_oracle(vqt, oracle_default):
+    k = vqt.kernel()
+    assert [g.window for g in k.window_groups] == [oracle_default.group(g)[0] for g in range(4)]
+    for g, wg in enumerate(k.window_groups):
+        _, K, Kn = oracle_default.group(g)
+        np.testing.assert_array_equal(wg.filter_bank.indices, K.indices)
+        np.testing.assert_allclose(wg.filter_bank.data.view(np.float32), K.data.view(np.float32), rtol=3e-7, atol=1e-12)
+        assert (wg.negative_filter_bank is None) == (Kn.nnz == 0)
+
+
+def test_fft_stage_against_numpy(vqt, chords):
+    # the FFT kernel alone, on the consumed bins, against a float64 FFT (cuFFT/pocketfft = test oracle only)
+    n_frames = 5
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_audio.upload(audio)
+    stride = vqt.spec_stride
+    d_spec = pv.DeviceBuffer(vqt, n_frames * stride * 8)
+    pv.fft_device(vqt, d_audio, 1, 0, HOP, n_frames, d_spec)
+    spec = d_spec.download((n_frames, stride), np.complex64)
+    for g, wg in enumerate(vqt.kernel().window_groups):
+        first, n_cols, off = vqt.group_columns(g)
+        wb, we = wg.window
+        for t in range(n_frames):
+            ref = np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))[first:first + n_cols]
+            got = spec[t, off:off + n_cols].astype(np.complex128)
+            scale = np.abs(np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))).max()
+            assert np.abs(got - ref).max() <= 2e-6 * scale, (g, t)
+
+
+def test_batch_against_oracle(vqt, oracle_default, chords):
+    got = vqt.calculate_vqt_batch_in_db(chords, HOP)
+    n_frames = synth.frames_in(chords.shape[0], vqt.n_fft, HOP)
+    assert got.shape == (n_frames, 588) and n_frames == 391
+    ref = oracle_default.calculate_batch_db(chords, HOP, mode=0)
+    assert np.all(np.isfinite(got)) and got.min() >= 0.0
+    assert np.abs(got - ref).max() <= TOL_DB
+
+
+def test_power_parity_above_minus_80_db(vqt, oracle_default, chords):
+    n_frames = 64
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_audio.upload(audio)
+    d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+    d_pow = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+    pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, d_pow)
+    p_gpu = d_pow.download((n_frames, 588))
+    p_ref = np.stack([oracle_default.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft], 0, True)[1]
+                      for t in range(n_frames)])
+    assert _power_err_db(p_gpu, p_ref) <= TOL_DB
+    # and the dB epilogue applied by the oracle to the GPU's own power reproduces the GPU output
+    db_gpu = d_out.download((n_frames, 588))
+    db_from_pow = np.stack([orc.power_to_db(p_gpu[t]) for t in range(n_frames)])
+    assert np.abs(db_gpu - db_from_pow).max() <= 2e-5
+
+
+def test_frames_streams_and_instant_are_bit_identical(vqt, chords):
+    n_frames = 40
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    batch = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    frames = np.stack([audio[t * HOP:t * HOP + vqt.n_fft] for t in range(n_frames)])
+    np.testing.assert_array_equal(vqt.calculate_vqt_frames_in_db(frames), batch)
+    for t in (0, 17, n_frames - 1):
+        np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(frames[t]), batch[t])
+    # streams: 3 recordings of different content, each equals its own batch call
+    n = vqt.n_fft + 9 * HOP
+    streams = np.stack([chords[o:o + n] for o in (0, 5000, 12345)])
+    out = vqt.calculate_vqt_streams_in_db(streams, HOP)
+    assert out.shape == (3, 10, 588)
+    for s in range(3):
+        np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+
+
+def test_edge_cases(vqt):
+    n_fft = vqt.n_fft
+    # silence -> all zeros (vqt.rs:944-951, second regime)
+    assert np.all(vqt.calculate_vqt_instant_in_db(np.zeros(n_fft, np.float32)) == 0.0)
+    # wrong length -> the reference panics (vqt.rs:867-871)
+    with pytest.raises(ValueError):
+        vqt.calculate_vqt_instant_in_db(np.zeros(n_fft - 1, np.float32))
+    with pytest.raises(ValueError):
+        vqt.calculate_vqt_batch_in_db(np.zeros(n_fft + 10, np.float32), 368, n_frames=2)
+    # empty and ragged
+    assert vqt.calculate_vqt_batch_in_db(np.zeros(100, np.float32), 368).shape == (0, 588)
+    rng = np.random.default_rng(5)
+    audio = (0.1 * rng.standard_normal(n_fft + 2 * 368 + 100)).astype(np.float32)   # 100 trailing samples unused
+    out = vqt.calculate_vqt_batch_in_db(audio, 368)
+    assert out.shape == (3, 588)
+    np.testing.assert_array_equal(out[2], vqt.calculate_vqt_instant_in_db(audio[736:736 + n_fft]))
+    # hop 1 and a non-multiple-of-tile frame count (tile = 8 frames, FFT CTAs hold 1/2/4/8 frames)
+    out1 = vqt.calculate_vqt_batch_in_db(audio[:n_fft + 12], 1)
+    assert out1.shape == (13, 588)
+    np.testing.assert_array_equal(out1[12], vqt.calculate_vqt_instant_in_db(audio[12:12 + n_fft]))
+    # only the union window [first_sample_used, n_fft) is read: garbage before it changes nothing
+    first = int(_ffi.load().pvqt_first_sample_used(vqt.handle))
+    assert first == 24576
+    a = audio[:n_fft].copy()
+    b = a.copy()
+    b[:first] = 1e6
+    np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(a), vqt.calculate_vqt_instant_in_db(b))
+
+
+def test_loud_and_quiet_regimes(vqt, oracle_default):
+    # power_to_db has two regimes (log_spec_min > 0 or not, vqt.rs:946-950): exercise both
+    x = orc.test_create_sines(oracle_default.params, [220, 440, 660])
+    for gain in (1e-4, 1e-2, 1.0, 30.0):
+        xs = (x * np.float32(gain)).astype(np.float32)
+        xs += (np.float32(gain) * 0.05 * np.random.default_rng(0).standard_normal(xs.shape[0])).astype(np.float32)
+        got = vqt.calculate_vqt_instant_in_db(xs)
+        ref = oracle_default.calculate_vqt_instant_in_db(xs, 0)
+        assert np.abs(got - ref).max() <= TOL_DB, gain
+
+
+def test_linearity_property_full_size(vqt):
+    """BASELINE configs[1] at full size (60 s, 3507 frames): size-independent properties.
+    Scaling the input by 2 multiplies every power by 4 (exact in binary floating point), so the
+    unclamped dB values shift by the same constant in every bin of a frame."""
+    audio = synth.polyphonic_chords(60.0, 22050.0, seed=0)
+    n_frames = synth.frames_in(audio.shape[0], vqt.n_fft, HOP)
+    assert n_frames == 3507
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+    d_pow = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+    d_audio.upload(audio)
+    pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, d_pow)
+    p1 = d_pow.download((n_frames, 588))
+    db1 = d_out.download((n_frames, 588))
+    d_audio.upload((audio * np.float32(2.0)).astype(np.float32))
+    pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, d_pow)
+    p2 = d_pow.download((n_frames, 588))
+    np.testing.assert_array_equal(p2, p1 * np.float32(4.0))
+    assert np.all(np.isfinite(db1)) and db1.min() >= 0.0 and db1.max() <= 60.0 + 1e-3
+    # host-buffer entry == device-resident entry, bit for bit
+    np.testing.assert_array_equal(vqt.calculate_vqt_batch_in_db(audio, HOP), db1)
+    # a frame of the long run equals the per-frame entry point on the same samples
+    for t in (0, 1234, 3506):
+        np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft]), db1[t])
+
+
+def test_hires_config(built_lib):
+    # BASELINE configs[3]: more buckets per octave, an extra octave, 2x FFT window
+    v = pv.Vqt(pv.VqtParameters.hires())
+    try:
+        assert v.n_buckets == 1344 and v.n_fft == 65536
+        o = _oracle_on_product_kernel(v, orc.hires_params())
+        audio = synth.polyphonic_chords(2.0, 44100.0, seed=4)
+        n_frames = synth.frames_in(audio.shape[0], v.n_fft, synth.HOP_HIRES)
+        got = v.calculate_vqt_batch_in_db(audio, synth.HOP_HIRES)
+        ref = o.calculate_batch_db(audio, synth.HOP_HIRES, mode=0)
+        assert got.shape == (n_frames, 1344)
+        assert np.abs(got - ref).max() <= TOL_DB
+    finally:
+        v.close()
+
+
+@pytest.mark.parametrize("n_fft,octaves,bpo", [(4096, 2, 24), (8192, 5, 36), (16384, 6, 48)])
+def test_other_parameter_sets(built_lib, n_fft, octaves, bpo):
+    # smaller FFT plans (window groups down to 128 samples) and the train.rs resolution
+    pp = pv.VqtParameters(n_fft=n_fft, range=pv.VqtRange(110.0, octaves, bpo), quality=1.0, gamma=20.0)
+    op = orc.make_params(n_fft=n_fft, min_freq=110.0, octaves=octaves, buckets_per_octave=bpo, quality=1.0, gamma=20.0)
+    v = pv.Vqt(pp)
+    try:
+        o = orc.OracleVqt(op)
+        rng = np.random.default_rng(n_fft)
+        audio = (0.05 * rng.standard_normal(n_fft + 20 * 100)).astype(np.float32)
+        t = np.arange(audio.shape[0]) / 22050.0
+        audio += (0.1 * np.sin(2 * np.pi * 523.25 * t)).astype(np.float32)
+        got = v.calculate_vqt_batch_in_db(audio, 100)
+        ref = o.calculate_batch_db(audio, 100, mode=0)
+        assert got.shape == ref.shape == (21, octaves * bpo)
+        assert np.abs(got - ref).max() <= TOL_DB
+    finally:
+        v.close()
+
+
+def test_multi_gpu_single_process_matches_single(built_lib, vqt, chords):
+    n = C.c_int()
+    _ffi.load().pvqt_device_count(C.byref(n))
+    devices = list(range(n.value))
+    m = pv.MultiVqt(pv.VqtParameters.default(), devices if len(devices) > 1 else [0, 0])
+    try:
+        np.testing.assert_array_equal(m.calculate_vqt_batch_in_db(chords, HOP),
+                                      vqt.calculate_vqt_batch_in_db(chords, HOP))
+        nsm = vqt.n_fft + 4 * HOP
+        streams = np.stack([chords[o:o + nsm] for o in (0, 1000, 2000, 3000, 4000)])
+        np.testing.assert_array_equal(m.calculate_vqt_streams_in_db(streams, HOP),
+                                      vqt.calculate_vqt_streams_in_db(streams, HOP))
+    finally:
+        m.close()
