@@ -266,9 +266,9 @@ def main():
     chk(lib.pvqt_set_profiling(h, 1))
     for _ in range(args.steps):
         flush(); step()
-    fft_ms, spmm_ms = C.c_double(), C.c_double()
-    fft_n, spmm_n = C.c_uint64(), C.c_uint64()
-    chk(lib.pvqt_get_profile(h, 1, C.byref(fft_ms), C.byref(fft_n), C.byref(spmm_ms), C.byref(spmm_n)))
+    k_ms = (C.c_double * 3)()
+    k_n = (C.c_uint64 * 3)()
+    chk(lib.pvqt_get_profile(h, 1, k_ms, k_n))
     chk(lib.pvqt_set_profiling(h, 0))
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------
@@ -283,7 +283,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        flush()
+        # no L2 flush here: every step's input arrives from pinned host memory through H2D copies
         chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
     pv.synchronize(vqt)
     e2e_s = time.perf_counter() - t0
@@ -305,8 +305,8 @@ def main():
         first = int(lib.pvqt_first_sample_used(h))
         union = params.n_fft - first
         bytes_per_frame = 4 * union + 4 * nb                      # 35,120 B at the defaults
-        fft_avg_ms = fft_ms.value / max(1, fft_n.value)
-        frames_per_launch = n_frames * args.steps / max(1, fft_n.value)
+        fft_avg_ms = k_ms[0] / max(1, k_n[0])
+        frames_per_launch = n_frames * args.steps / max(1, k_n[0])
         peak, peak_src = measured_peak_gbs()
         achieved = bytes_per_frame * frames_per_launch / (fft_avg_ms * 1e-3) / 1e9
         whole = bytes_per_frame * n_frames / (statistics.median(step_ms) * 1e-3) / 1e9
@@ -330,8 +330,9 @@ def main():
                 "bound": "hbm", "kernel": "fft_groups_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": bytes_per_frame, "frames_per_launch": frames_per_launch,
-                "kernel_avg_ms": fft_avg_ms, "kernel_share_of_step": fft_ms.value / max(1e-9, fft_ms.value + spmm_ms.value),
-                "spmm_db_avg_ms": spmm_ms.value / max(1, spmm_n.value),
+                "kernel_avg_ms": fft_avg_ms, "kernel_share_of_step": k_ms[0] / max(1e-9, sum(k_ms)),
+                "other_kernels_avg_ms": {"spmm_kernel": k_ms[1] / max(1, k_n[1]),
+                                         "power_to_db_kernel": k_ms[2] / max(1, k_n[2])},
                 "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                 "note": "the path is FP32/shared-memory bound (SURVEY.md 8d); HBM fraction reported as BASELINE asks",
             },

@@ -154,11 +154,14 @@ size_t pvqt_frames_in(const pvqt *v, size_t n_samples, size_t hop);
 int pvqt_calc_db_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride,
                         size_t hop, size_t frames_per_stream, float *d_out, float *d_power,
                         void *cuda_stream);
-/* Test hook: spectra of the window groups restricted to the consumed columns.
- * d_spec: [n_frames][pvqt_spec_stride(v)] complex (re,im) floats. */
+/* Test hook: spectra of the window groups restricted to the consumed columns, in the library's
+ * tiled planar scratch layout: [tile = frame / 8][column < pvqt_spec_stride(v)][16 floats], a 64-byte
+ * record per (tile, column) with logical 16-byte chunks 0,1 = Re of frames 0-3, 4-7 and 2,3 = Im of
+ * frames 0-3, 4-7; logical chunk q is stored at physical chunk q ^ ((column >> 1) & 3).
+ * d_spec: ceil(n_frames / 8) tiles. */
 int    pvqt_fft_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
                        size_t frames_per_stream, float *d_spec, void *cuda_stream);
-size_t pvqt_spec_stride(const pvqt *v);                 /* complex elements per frame */
+size_t pvqt_spec_stride(const pvqt *v);                 /* columns per tile */
 int    pvqt_group_columns(const pvqt *v, size_t group, uint32_t *first_col, uint32_t *n_cols,
                           uint32_t *spec_offset);       /* consumed FFT bins of a group */
 
@@ -178,11 +181,10 @@ int pvqt_event_elapsed_ms(pvqt *v, void *start, void *stop, float *ms); /* synch
 /* Number of kernel launches this handle has issued since creation. */
 uint64_t pvqt_launch_count(const pvqt *v);
 /* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
- * launching stream.  pvqt_get_profile synchronises and returns the summed durations and
- * launch counts of K-fft and K-spmm since the last reset. */
+ * launching stream.  pvqt_get_profile synchronises and returns the summed durations and launch
+ * counts since the last reset, indexed 0 = K-fft, 1 = K-spmm, 2 = K-db. */
 int pvqt_set_profiling(pvqt *v, int enabled);
-int pvqt_get_profile(pvqt *v, int reset, double *fft_ms, uint64_t *fft_launches, double *spmm_ms,
-                     uint64_t *spmm_launches);
+int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms /*[3]*/, uint64_t *kernel_launches /*[3]*/);
 
 /* ---- sharding (frame ranges / streams, no collective) ---------- */
 /* Split `n_units` (frames or streams) into `n_parts` contiguous, balanced ranges.  Pure

@@ -112,8 +112,7 @@ SIGNATURES = {
     "pvqt_event_elapsed_ms": (C.c_int, [_VP, _VP, _VP, C.POINTER(C.c_float)]),
     "pvqt_launch_count": (C.c_uint64, [_VP]),
     "pvqt_set_profiling": (C.c_int, [_VP, C.c_int]),
-    "pvqt_get_profile": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
-                                   C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "pvqt_get_profile": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pvqt_shard_range": (C.c_int, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "pvqt_frame_range_samples": (C.c_int, [_SZ, _SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "pvqt_multi_create": (C.c_int, [C.POINTER(PvqtParams), C.c_int, C.POINTER(C.c_int), C.POINTER(_VP),

@@ -87,21 +87,24 @@ struct pvqt {
     pvqt_params params{};
     pvqt_host::Kernel kernel;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // compute (and device-pointer entry points)
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // host->device / device->host copies of the host entry points
+    std::vector<cudaEvent_t> events;         // pipeline edges, reused across calls
+    size_t staging_budget_samples = (size_t)256 << 20;  // device audio per super-batch (1 GiB)
 
     // device plan
     std::vector<void *> owned;          // device allocations freed on destroy
     FftParams fft{};                    // template (frames/spec filled per launch)
     SpmmParams spmm{};
     int fft_block_threads = 256;
-    int spmm_frames_per_cta = 8;
+    float ref_db = 0.0f;
     std::vector<uint32_t> col_lo, n_cols, spec_off;
     size_t first_sample_used = 0;
     size_t last_sample_used = 0;        // one past
     uint32_t chunk_frames = 8192;
 
     // scratch
-    DeviceBuffer spec, d_audio, d_out;
+    DeviceBuffer spec, power, d_audio, d_out;
     std::atomic<uint64_t> launches{0};
 
     // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
@@ -200,86 +203,117 @@ int build_device_plan(pvqt *v)
         cudaError_t e = upload(v, st, &d.split_twiddle);
         if (e != cudaSuccess) return cuda_fail(e, "upload split twiddles");
     }
-    F.spec_stride = (spec_cursor + 1) & ~1;  // even: frame rows stay 16-byte aligned
+    F.spec_stride = (spec_cursor + 7) & ~7;  // whole 8-column groups: row blocks stage from a multiple of 8
 
-    // ---- banded sliced-ELL layout of the spectral kernel ------------------------------
+    // ---- banded layout of the spectral kernel: 64-row blocks, two adjacent rows per lane ----
+    struct Row { int col0 = 0, len = 0, ncol0 = 0, nlen = 0; const pvqt_host::Csr *m = nullptr, *mn = nullptr; int local = 0; };
     const int nb = (int)v->kernel.n_buckets;
-    const int n_blocks = (nb + kSpmmRowsPerBlock - 1) / kSpmmRowsPerBlock;
-    struct RowBand { int col0 = 0, len = 0, ncol0 = 0, nlen = 0; const pvqt_host::Csr *m = nullptr, *mn = nullptr; int local = 0; int spec = 0; int lo = 0; };
-    std::vector<RowBand> rows((size_t)n_blocks * kSpmmRowsPerBlock);
-    {
-        int row = 0;
-        for (size_t gi = 0; gi < groups.size(); ++gi) {
-            const auto &g = groups[gi];
-            for (int r = 0; r < g.filter_bank.rows; ++r, ++row) {
-                RowBand &b = rows[row];
-                b.m = &g.filter_bank; b.mn = &g.negative_filter_bank; b.local = r;
-                b.spec = F.group[gi].spec_offset; b.lo = F.group[gi].col_lo;
+    std::vector<SpmmRowBlock> blocks;
+    std::vector<int4> lane_meta;
+    std::vector<float4> values;
+    int max_cols = 8;
+    int first_row = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const auto &g = groups[gi];
+        const int spec = F.group[gi].spec_offset, lo = F.group[gi].col_lo;
+        const int rows_in_group = g.filter_bank.rows;
+        for (int r0 = 0; r0 < rows_in_group; r0 += kRowsPerBlock) {
+            const int n_rows = std::min(kRowsPerBlock, rows_in_group - r0);
+            Row rows[kRowsPerBlock];
+            for (int i = 0; i < n_rows; ++i) {
+                Row &rw = rows[i];
+                const int r = r0 + i;
+                rw.m = &g.filter_bank; rw.mn = &g.negative_filter_bank; rw.local = r;
                 const int s = g.filter_bank.indptr[r], e = g.filter_bank.indptr[r + 1];
-                if (e > s) {
-                    b.col0 = g.filter_bank.indices[s];
-                    b.len = g.filter_bank.indices[e - 1] - b.col0 + 1;
-                }
+                if (e > s) { rw.col0 = spec + g.filter_bank.indices[s] - lo; rw.len = g.filter_bank.indices[e - 1] - g.filter_bank.indices[s] + 1; }
                 if (g.negative_filter_bank.nnz() > 0) {
                     const int ns_ = g.negative_filter_bank.indptr[r], ne = g.negative_filter_bank.indptr[r + 1];
                     if (ne > ns_) {
-                        b.ncol0 = g.negative_filter_bank.indices[ns_];
-                        b.nlen = g.negative_filter_bank.indices[ne - 1] - b.ncol0 + 1;
+                        rw.ncol0 = spec + g.negative_filter_bank.indices[ns_] - lo;
+                        rw.nlen = g.negative_filter_bank.indices[ne - 1] - g.negative_filter_bank.indices[ns_] + 1;
                     }
                 }
             }
-        }
-        if (row != nb) return fail(PVQT_PANIC, "kernel rows do not add up to n_buckets");
-    }
-    std::vector<SpmmBlock> blocks(n_blocks);
-    std::vector<int2> row_cols(rows.size(), make_int2(0, 0));
-    std::vector<float2> values;
-    for (int b = 0; b < n_blocks; ++b) {
-        int w = 0, nw = 0;
-        for (int l = 0; l < kSpmmRowsPerBlock; ++l) {
-            w = std::max(w, rows[(size_t)b * kSpmmRowsPerBlock + l].len);
-            nw = std::max(nw, rows[(size_t)b * kSpmmRowsPerBlock + l].nlen);
-        }
-        blocks[b].val_base = (int)(values.size() / kSpmmRowsPerBlock);
-        blocks[b].width = w;
-        values.resize(values.size() + (size_t)w * kSpmmRowsPerBlock, make_float2(0.f, 0.f));
-        blocks[b].nval_base = (int)(values.size() / kSpmmRowsPerBlock);
-        blocks[b].nwidth = nw;
-        values.resize(values.size() + (size_t)nw * kSpmmRowsPerBlock, make_float2(0.f, 0.f));
-        for (int l = 0; l < kSpmmRowsPerBlock; ++l) {
-            const size_t ri = (size_t)b * kSpmmRowsPerBlock + l;
-            const RowBand &rb = rows[ri];
-            if (!rb.m) continue;
-            // rows without a (conjugate) band still run the block's loop over zero coefficients:
-            // point them at a valid column
-            row_cols[ri] = make_int2(rb.len > 0 ? rb.spec + (rb.col0 - rb.lo) : rb.spec,
-                                     rb.nlen > 0 ? rb.spec + (rb.ncol0 - rb.lo) : rb.spec);
-            for (int e = rb.m->indptr[rb.local]; e < rb.m->indptr[rb.local + 1]; ++e) {
-                const int j = rb.m->indices[e] - rb.col0;
-                values[((size_t)blocks[b].val_base + j) * kSpmmRowsPerBlock + l] =
-                    make_float2(rb.m->data[e].real(), rb.m->data[e].imag());
-            }
-            if (rb.nlen > 0)
-                for (int e = rb.mn->indptr[rb.local]; e < rb.mn->indptr[rb.local + 1]; ++e) {
-                    const int j = rb.mn->indices[e] - rb.ncol0;
-                    // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg)
-                    values[((size_t)blocks[b].nval_base + j) * kSpmmRowsPerBlock + l] =
-                        make_float2(rb.mn->data[e].real(), -rb.mn->data[e].imag());
+            // per lane: the union band of its two rows
+            struct Pair { int col0 = 0, len = 0, ncol0 = 0, nlen = 0; };
+            Pair pairs[32];
+            int width = 0, nwidth = 0, cmin = 1 << 30, cmax = -1;
+            for (int l = 0; l < 32; ++l) {
+                int a0 = 1 << 30, a1 = -1, n0 = 1 << 30, n1 = -1;
+                for (int q = 0; q < kRowsPerLane; ++q) {
+                    const Row &rw = rows[kRowsPerLane * l + q];
+                    if (rw.len > 0) { a0 = std::min(a0, rw.col0); a1 = std::max(a1, rw.col0 + rw.len); }
+                    if (rw.nlen > 0) { n0 = std::min(n0, rw.ncol0); n1 = std::max(n1, rw.ncol0 + rw.nlen); }
                 }
+                if (a1 >= 0) { pairs[l].col0 = a0; pairs[l].len = a1 - a0; cmin = std::min(cmin, a0); cmax = std::max(cmax, a1); }
+                if (n1 >= 0) { pairs[l].ncol0 = n0; pairs[l].nlen = n1 - n0; cmin = std::min(cmin, n0); cmax = std::max(cmax, n1); }
+                width = std::max(width, pairs[l].len);
+                nwidth = std::max(nwidth, pairs[l].nlen);
+            }
+            if (cmax < 0) { cmin = 0; cmax = 1; }
+            width = (width + kSpmmUnroll - 1) / kSpmmUnroll * kSpmmUnroll;  // zero-padded, see spmm_kernel
+            SpmmRowBlock B{};
+            B.first_row = first_row + r0;
+            B.n_rows = n_rows;
+            B.width = width;
+            B.nwidth = nwidth;
+            B.col_lo = cmin & ~7;
+            B.n_cols = cmax - B.col_lo;
+            B.val_base = (int)(values.size() / 32);
+            values.resize(values.size() + (size_t)width * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+            B.nval_base = (int)(values.size() / 32);
+            values.resize(values.size() + (size_t)nwidth * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+            max_cols = std::max(max_cols, B.n_cols);
+            for (int l = 0; l < 32; ++l) {
+                const Pair &pr = pairs[l];
+                // lanes without a (conjugate) band run zero trips; keep their column inside the staged range
+                lane_meta.push_back(make_int4(pr.len > 0 ? pr.col0 - B.col_lo : 0, pr.len,
+                                              pr.nlen > 0 ? pr.ncol0 - B.col_lo : 0, pr.nlen));
+                for (int q = 0; q < kRowsPerLane; ++q) {
+                    const Row &rw = rows[kRowsPerLane * l + q];
+                    if (!rw.m) continue;
+                    for (int e = rw.m->indptr[rw.local]; e < rw.m->indptr[rw.local + 1]; ++e) {
+                        const int j = spec + rw.m->indices[e] - lo - pr.col0;
+                        float4 &slot = values[((size_t)B.val_base + j) * 32 + l];
+                        (q == 0 ? slot.x : slot.z) = rw.m->data[e].real();
+                        (q == 0 ? slot.y : slot.w) = rw.m->data[e].imag();
+                    }
+                    if (rw.nlen > 0)
+                        for (int e = rw.mn->indptr[rw.local]; e < rw.mn->indptr[rw.local + 1]; ++e) {
+                            const int j = spec + rw.mn->indices[e] - lo - pr.ncol0;
+                            float4 &slot = values[((size_t)B.nval_base + j) * 32 + l];
+                            // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg)
+                            (q == 0 ? slot.x : slot.z) = rw.mn->data[e].real();
+                            (q == 0 ? slot.y : slot.w) = -rw.mn->data[e].imag();
+                        }
+                }
+            }
+            blocks.push_back(B);
         }
+        first_row += rows_in_group;
     }
+    if (first_row != nb) return fail(PVQT_PANIC, "kernel rows do not add up to n_buckets");
+    values.resize(values.size() + (size_t)kSpmmUnroll * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
+
     SpmmParams &S = v->spmm;
     std::memset(&S, 0, sizeof(S));
     cudaError_t e;
     if ((e = upload(v, blocks, &S.blocks)) != cudaSuccess) return cuda_fail(e, "upload blocks");
-    if ((e = upload(v, row_cols, &S.row_cols)) != cudaSuccess) return cuda_fail(e, "upload row_cols");
+    if ((e = upload(v, lane_meta, &S.lane_meta)) != cudaSuccess) return cuda_fail(e, "upload lane_meta");
     if ((e = upload(v, values, &S.values)) != cudaSuccess) return cuda_fail(e, "upload values");
-    S.n_blocks = n_blocks;
+    std::vector<int32_t> order(blocks.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return blocks[x].width + blocks[x].nwidth > blocks[y].width + blocks[y].nwidth;
+    });
+    if ((e = upload(v, order, &S.block_order)) != cudaSuccess) return cuda_fail(e, "upload block order");
+    S.n_blocks = (int)blocks.size();
     S.n_buckets = nb;
     S.spec_stride = F.spec_stride;
-    S.ref_db = 10.0f * std::log10(0.3f * 0.3f);  // vqt.rs:923,927
+    S.max_cols = max_cols;
+    v->ref_db = 10.0f * std::log10(0.3f * 0.3f);  // vqt.rs:923,927
 
-    if ((e = configure_kernels(F.spec_stride, nb, &v->spmm_frames_per_cta)) != cudaSuccess)
+    if ((e = configure_kernels(max_cols)) != cudaSuccess)
         return cuda_fail(e, "configure kernels (is this an sm_100a device?)");
     return PVQT_OK;
 }
@@ -300,7 +334,7 @@ void prof_end(pvqt *v, cudaStream_t stream)
     cudaEventRecord(v->timed.back().b, stream);
 }
 
-// Launch FFT + SpMM/dB for `n_frames` frames laid out as `layout` describes.
+// Launch K-fft, K-spmm and K-db for the frames `(n_streams, frames_per_stream, hop)` describe.
 int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
                size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream)
 {
@@ -308,10 +342,22 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     if (total == 0) return PVQT_OK;
     if (frames_per_stream > 0xffffffffull) return fail(PVQT_INVALID_ARGUMENT, "frames_per_stream too large");
     const size_t nb = v->kernel.n_buckets;
-    const uint32_t chunk = v->chunk_frames;
+    const uint32_t chunk = v->chunk_frames;  // multiple of kTileFrames
+    const size_t chunk_now = std::min<size_t>(total, chunk);
+    const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
     if (!d_spec_out) {
-        cudaError_t e = v->spec.reserve((size_t)std::min<size_t>(total, chunk) * v->fft.spec_stride * sizeof(float2));
-        if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
+        const size_t want = ((chunk_now + kTileFrames - 1) / kTileFrames) * tile_elems * sizeof(float);
+        if (want > v->spec.bytes) {
+            cudaError_t e = v->spec.reserve(want);
+            if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
+            // frames past the end of the last tile are never written: keep them finite
+            if ((e = cudaMemsetAsync(v->spec.ptr, 0, v->spec.bytes, stream)) != cudaSuccess)
+                return cuda_fail(e, "clear spectrum scratch");
+        }
+        if (!d_power) {
+            cudaError_t e = v->power.reserve(chunk_now * nb * sizeof(float));
+            if (e != cudaSuccess) return cuda_fail(e, "allocate power scratch");
+        }
     }
     for (size_t f0 = 0; f0 < total; f0 += chunk) {
         const uint32_t n = (uint32_t)std::min<size_t>(chunk, total - f0);
@@ -322,8 +368,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
         fp.frames.frames_per_stream = (uint32_t)frames_per_stream;
         fp.frames.n_frames = n;
         fp.frames.first_frame = f0;
-        fp.spec = d_spec_out ? reinterpret_cast<float2 *>(d_spec_out) + f0 * fp.spec_stride
-                             : static_cast<float2 *>(v->spec.ptr);
+        fp.spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(v->spec.ptr);
         int ctas = 0;
         for (int g = 0; g < fp.n_groups; ++g) {
             fp.group[g].cta_begin = ctas;
@@ -338,20 +383,35 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
 
         SpmmParams sp = v->spmm;
         sp.n_frames = n;
+        sp.n_tiles = (n + kTileFrames - 1) / kTileFrames;
         sp.spec = fp.spec;
-        sp.out_db = d_out + f0 * nb;
-        sp.out_power = d_power ? d_power + f0 * nb : nullptr;
+        sp.power = d_power ? d_power + f0 * nb : static_cast<float *>(v->power.ptr);
         prof_begin(v, 1, stream);
-        e = launch_spmm_db(sp, v->spmm_frames_per_cta, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_kernel");
+        e = launch_spmm(sp, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch spmm_kernel");
+        prof_end(v, stream);
+        v->launches.fetch_add(1);
+
+        DbParams dp{};
+        dp.power = sp.power;
+        dp.out_db = d_out + f0 * nb;
+        dp.n_frames = n;
+        dp.n_buckets = (int32_t)nb;
+        dp.ref_db = v->ref_db;
+        prof_begin(v, 2, stream);
+        e = launch_power_to_db(dp, stream);
+        if (e != cudaSuccess) return cuda_fail(e, "launch power_to_db_kernel");
         prof_end(v, stream);
         v->launches.fetch_add(1);
     }
     return PVQT_OK;
 }
 
-// Host buffers in/out.  Streams are processed in segments whose audio fits the staging budget;
-// a stream longer than the budget is cut into frame ranges (halo of n_fft - hop samples).
+// Host buffers in/out, pipelined: the work is cut into segments (stream ranges, or frame ranges of one
+// long recording); segment i+1's host->device copy and segment i-1's device->host copy run on their
+// own streams while segment i computes.  Every segment owns a distinct region of the device audio /
+// output buffers, so the three streams only need the event edges H2D(i) -> compute(i) -> D2H(i).
+// Work larger than the staging budget is processed in consecutive super-batches.
 int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples, size_t hop,
              size_t frames_per_stream, float *out)
 {
@@ -365,41 +425,102 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
     PVQT_CUDA(cudaSetDevice(v->device));
 
-    const size_t budget = (size_t)128 << 20;  // samples per staged segment (512 MiB)
+    const size_t budget = v->staging_budget_samples;            // device audio per super-batch
     const size_t span = (frames_per_stream - 1) * hop + n_fft;  // samples one stream needs
-    if (span <= budget) {
-        const size_t per_seg = std::max<size_t>(1, budget / span);
+    size_t ev_used = 0;
+    auto next_event = [&](cudaEvent_t *e) -> cudaError_t {
+        if (ev_used == v->events.size()) {
+            cudaEvent_t ne;
+            cudaError_t rc = cudaEventCreateWithFlags(&ne, cudaEventDisableTiming);
+            if (rc != cudaSuccess) return rc;
+            v->events.push_back(ne);
+        }
+        *e = v->events[ev_used++];
+        return cudaSuccess;
+    };
+    auto segment_frames = [&](size_t frames_in_batch) {
+        // ~6 segments per batch, at least 256 and at most one kernel chunk of frames each
+        return std::min<size_t>(std::max<size_t>((frames_in_batch + 5) / 6, 256), v->chunk_frames);
+    };
+    // one pipelined segment: copy in (s_in), compute (stream), copy out (s_out)
+    auto compute_and_copy_out = [&](cudaEvent_t copied, const float *d_audio, size_t ns, size_t dstride, size_t nf,
+                                    float *d_out, float *h_out) -> int {
+        PVQT_CUDA(cudaStreamWaitEvent(v->stream, copied, 0));
+        int rc = run_device(v, d_audio, ns, dstride, hop, nf, d_out, nullptr, nullptr, v->stream);
+        if (rc) return rc;
+        cudaEvent_t done;
+        PVQT_CUDA(next_event(&done));
+        PVQT_CUDA(cudaEventRecord(done, v->stream));
+        PVQT_CUDA(cudaStreamWaitEvent(v->s_out, done, 0));
+        PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
+        return PVQT_OK;
+    };
+    auto drain = [&]() -> int {
+        PVQT_CUDA(cudaStreamSynchronize(v->s_in));
+        PVQT_CUDA(cudaStreamSynchronize(v->stream));
+        PVQT_CUDA(cudaStreamSynchronize(v->s_out));
+        ev_used = 0;
+        return PVQT_OK;
+    };
+
+    if (span <= budget && (n_streams > 1 || frames_per_stream <= 256)) {
+        // ---- stream-sharded: whole streams per segment -----------------------------------------------
         const size_t dstride = (span + 3) & ~(size_t)3;
-        for (size_t s0 = 0; s0 < n_streams; s0 += per_seg) {
-            const size_t ns = std::min(per_seg, n_streams - s0);
-            PVQT_CUDA(v->d_audio.reserve(ns * dstride * sizeof(float)));
-            PVQT_CUDA(v->d_out.reserve(ns * frames_per_stream * nb * sizeof(float)));
-            PVQT_CUDA(cudaMemcpy2DAsync(v->d_audio.ptr, dstride * sizeof(float), audio + s0 * stream_stride,
-                                        stream_stride * sizeof(float), span * sizeof(float), ns,
-                                        cudaMemcpyHostToDevice, v->stream));
-            int rc = run_device(v, static_cast<const float *>(v->d_audio.ptr), ns, dstride, hop, frames_per_stream,
-                                static_cast<float *>(v->d_out.ptr), nullptr, nullptr, v->stream);
+        const size_t per_batch = std::max<size_t>(1, budget / dstride);
+        for (size_t b0 = 0; b0 < n_streams; b0 += per_batch) {
+            const size_t nbatch = std::min(per_batch, n_streams - b0);
+            PVQT_CUDA(v->d_audio.reserve(nbatch * dstride * sizeof(float)));
+            PVQT_CUDA(v->d_out.reserve(nbatch * frames_per_stream * nb * sizeof(float)));
+            float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
+            const size_t per_seg = std::max<size_t>(1, segment_frames(nbatch * frames_per_stream) / frames_per_stream);
+            for (size_t s0 = 0; s0 < nbatch; s0 += per_seg) {
+                const size_t ns = std::min(per_seg, nbatch - s0);
+                PVQT_CUDA(cudaMemcpy2DAsync(d_audio + s0 * dstride, dstride * sizeof(float),
+                                            audio + (b0 + s0) * stream_stride, stream_stride * sizeof(float),
+                                            span * sizeof(float), ns, cudaMemcpyHostToDevice, v->s_in));
+                cudaEvent_t copied;
+                PVQT_CUDA(next_event(&copied));
+                PVQT_CUDA(cudaEventRecord(copied, v->s_in));
+                int rc = compute_and_copy_out(copied, d_audio + s0 * dstride, ns, dstride, frames_per_stream,
+                                              d_out + s0 * frames_per_stream * nb,
+                                              out + (b0 + s0) * frames_per_stream * nb);
+                if (rc) return rc;
+            }
+            int rc = drain();
             if (rc) return rc;
-            PVQT_CUDA(cudaMemcpyAsync(out + s0 * frames_per_stream * nb, v->d_out.ptr,
-                                      ns * frames_per_stream * nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
-            PVQT_CUDA(cudaStreamSynchronize(v->stream));
         }
     } else {
-        const size_t frames_per_seg = std::max<size_t>(1, (budget - n_fft) / hop + 1);
+        // ---- frame-range sharded: one long recording at a time, each sample copied once ---------------
+        const size_t frames_per_batch = budget > n_fft ? std::max<size_t>(1, (budget - n_fft) / std::max<size_t>(hop, 1) + 1)
+                                                       : 1;
         for (size_t s = 0; s < n_streams; ++s) {
-            for (size_t f0 = 0; f0 < frames_per_stream; f0 += frames_per_seg) {
-                const size_t nf = std::min(frames_per_seg, frames_per_stream - f0);
-                const size_t seg_samples = (nf - 1) * hop + n_fft;
-                PVQT_CUDA(v->d_audio.reserve(seg_samples * sizeof(float)));
-                PVQT_CUDA(v->d_out.reserve(nf * nb * sizeof(float)));
-                PVQT_CUDA(cudaMemcpyAsync(v->d_audio.ptr, audio + s * stream_stride + f0 * hop,
-                                          seg_samples * sizeof(float), cudaMemcpyHostToDevice, v->stream));
-                int rc = run_device(v, static_cast<const float *>(v->d_audio.ptr), 1, 0, hop, nf,
-                                    static_cast<float *>(v->d_out.ptr), nullptr, nullptr, v->stream);
+            const float *h_audio = audio + s * stream_stride;
+            for (size_t b0 = 0; b0 < frames_per_stream; b0 += frames_per_batch) {
+                const size_t nbatch = std::min(frames_per_batch, frames_per_stream - b0);
+                const size_t batch_samples = (nbatch - 1) * hop + n_fft;
+                PVQT_CUDA(v->d_audio.reserve(batch_samples * sizeof(float)));
+                PVQT_CUDA(v->d_out.reserve(nbatch * nb * sizeof(float)));
+                float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
+                const size_t per_seg = segment_frames(nbatch);
+                size_t copied_samples = 0;  // samples of this batch already on the device
+                for (size_t f0 = 0; f0 < nbatch; f0 += per_seg) {
+                    const size_t nf = std::min(per_seg, nbatch - f0);
+                    const size_t need = (f0 + nf - 1) * hop + n_fft;  // batch-relative end of this segment's samples
+                    if (need > copied_samples) {
+                        PVQT_CUDA(cudaMemcpyAsync(d_audio + copied_samples, h_audio + b0 * hop + copied_samples,
+                                                  (need - copied_samples) * sizeof(float), cudaMemcpyHostToDevice,
+                                                  v->s_in));
+                        copied_samples = need;
+                    }
+                    cudaEvent_t copied;
+                    PVQT_CUDA(next_event(&copied));
+                    PVQT_CUDA(cudaEventRecord(copied, v->s_in));
+                    int rc = compute_and_copy_out(copied, d_audio + f0 * hop, 1, 0, nf, d_out + f0 * nb,
+                                                  out + (s * frames_per_stream + b0 + f0) * nb);
+                    if (rc) return rc;
+                }
+                int rc = drain();
                 if (rc) return rc;
-                PVQT_CUDA(cudaMemcpyAsync(out + (s * frames_per_stream + f0) * nb, v->d_out.ptr,
-                                          nf * nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
-                PVQT_CUDA(cudaStreamSynchronize(v->stream));
             }
         }
     }
@@ -555,7 +676,9 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
     }
     if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_error(e, "cudaSetDevice");
     v->device = device;
-    if ((e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    if ((e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&v->s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking)) != cudaSuccess)
         return cuda_error(e, "cudaStreamCreate");
 
     pvqt *raw = v.release();
@@ -575,10 +698,13 @@ void pvqt_destroy(pvqt *v)
 {
     if (!v) return;
     cudaSetDevice(v->device);
-    if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+    for (cudaStream_t s : {v->s_in, v->stream, v->s_out})
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (cudaEvent_t e : v->events) cudaEventDestroy(e);
     for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (void *p : v->owned) cudaFree(p);
     v->spec.release();
+    v->power.release();
     v->d_audio.release();
     v->d_out.release();
     delete v;
@@ -767,13 +893,12 @@ int pvqt_set_profiling(pvqt *v, int enabled)
     return PVQT_OK;
 }
 
-int pvqt_get_profile(pvqt *v, int reset, double *fft_ms, uint64_t *fft_launches, double *spmm_ms,
-                     uint64_t *spmm_launches)
+int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms /*[3]*/, uint64_t *kernel_launches /*[3]*/)
 {
     if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
     PVQT_CUDA(cudaSetDevice(v->device));
-    double ms[2] = {0.0, 0.0};
-    uint64_t n[2] = {0, 0};
+    double ms[3] = {0.0, 0.0, 0.0};
+    uint64_t n[3] = {0, 0, 0};
     for (const auto &t : v->timed) {
         float e = 0.f;
         PVQT_CUDA(cudaEventSynchronize(t.b));
@@ -785,10 +910,10 @@ int pvqt_get_profile(pvqt *v, int reset, double *fft_ms, uint64_t *fft_launches,
         for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
         v->timed.clear();
     }
-    if (fft_ms) *fft_ms = ms[0];
-    if (fft_launches) *fft_launches = n[0];
-    if (spmm_ms) *spmm_ms = ms[1];
-    if (spmm_launches) *spmm_launches = n[1];
+    for (int i = 0; i < 3; ++i) {
+        if (kernel_ms) kernel_ms[i] = ms[i];
+        if (kernel_launches) kernel_launches[i] = n[i];
+    }
     return PVQT_OK;
 }
 

@@ -9,7 +9,30 @@ namespace pvqt_dev {
 constexpr int kMaxGroups = 8;          // window groups per Vqt (4 at the defaults, 5 hi-res)
 constexpr int kMaxFftPasses = 4;       // radix passes of the largest plan (N_c = 16384)
 constexpr int kPointsPerThread = 16;   // complex points each FFT thread keeps in registers
-constexpr int kSpmmRowsPerBlock = 32;  // rows of one sliced-ELL block (one row per lane)
+constexpr int kTileFrames = 8;         // frames per spectrum tile (one 64-byte record per column)
+constexpr int kRowsPerLane = 2;        // adjacent kernel rows one SpMM lane accumulates
+constexpr int kRowsPerBlock = 32 * kRowsPerLane;
+
+// Spectrum scratch layout ("tiled, planar"): [tile = frame / 8][column][re f0..f7 | im f0..f7] floats,
+// i.e. one 64-byte record per (tile, column) holding the real parts of the tile's 8 frames followed by
+// the imaginary parts.  SpMM lanes fetch a record with four LDS.128 and feed frame *pairs* to packed
+// FFMA2s with the kernel coefficient as the broadcast scalar -- no register shuffling.  The four
+// 16-byte chunks of a record are XOR-swizzled with bits 1..2 of the column so that lanes reading
+// consecutive columns never collide on a bank.  Position of (frame f, column c), in floats:
+__host__ __device__ inline size_t spec_index_re(size_t frame, int col, int spec_stride)
+{
+    const size_t tile = frame / kTileFrames;
+    const int fi = (int)(frame % kTileFrames);
+    const int chunk = (fi >> 2) ^ ((col >> 1) & 3);              // re: logical chunks 0,1; im: 2,3
+    return (tile * spec_stride + col) * (2 * kTileFrames) + (chunk << 2) + (fi & 3);
+}
+__host__ __device__ inline size_t spec_index_im(size_t frame, int col, int spec_stride)
+{
+    const size_t tile = frame / kTileFrames;
+    const int fi = (int)(frame % kTileFrames);
+    const int chunk = (2 + (fi >> 2)) ^ ((col >> 1) & 3);
+    return (tile * spec_stride + col) * (2 * kTileFrames) + (chunk << 2) + (fi & 3);
+}
 
 // One window group (WindowGroup, vqt.rs:388-404) as the FFT kernel sees it.
 struct FftGroup {
@@ -37,38 +60,57 @@ struct FrameLayout {
 struct FftParams {
     FftGroup    group[kMaxGroups];
     int32_t     n_groups;
-    int32_t     spec_stride;  // complex elements per frame in `spec`
+    int32_t     spec_stride;  // columns per tile (multiple of 8)
     FrameLayout frames;
-    float2     *spec;         // [n_frames][spec_stride]
+    float      *spec;         // tiled planar layout, ceil(n_frames / 8) tiles
 };
 
-// Sliced-ELL, zero-filled band layout of the spectral kernel (all groups concatenated,
-// rows in ascending frequency = output order).
-struct SpmmBlock {
-    int32_t val_base;   // first ELL slot of the positive band  (slot = 32 float2)
-    int32_t width;      // slots in the positive band
-    int32_t nval_base;  // first ELL slot of the conjugate-part band
-    int32_t nwidth;     // slots in the conjugate-part band (0 for most blocks)
+// The spectral kernel as the SpMM sees it: blocks of 64 consecutive rows of one window group, two
+// adjacent rows per lane.  A lane's two rows share one zero-filled band of columns
+// [pair_col0, pair_col0 + pair_len); slot j of a block holds, for each lane, the float4
+// (K[row0, c].re, K[row0, c].im, K[row1, c].re, K[row1, c].im) with c = pair_col0 + j.
+struct SpmmRowBlock {
+    int32_t first_row;   // output row of lane 0's first row
+    int32_t n_rows;      // valid rows in this block (<= 64)
+    int32_t width;       // slots of the band
+    int32_t nwidth;      // slots of the conjugate-part band
+    int32_t val_base;    // first slot of the band in `values` (slot = 32 float4)
+    int32_t nval_base;   // first slot of the conjugate-part band
+    int32_t col_lo;      // first spectrum column staged for this block (multiple of 8)
+    int32_t n_cols;      // columns staged
 };
 
 struct SpmmParams {
-    const SpmmBlock *blocks;     // n_blocks
-    const int2      *row_cols;   // per padded row: (first column of band, first column of conj band)
-    const float2    *values;     // ELL slots
+    const SpmmRowBlock *blocks;
+    const int4   *lane_meta;   // [block][lane]: (pair_col0 - col_lo, pair_len, npair_col0 - col_lo, npair_len)
+    const float4 *values;
     int32_t  n_blocks;
     int32_t  n_buckets;
     int32_t  spec_stride;
+    int32_t  max_cols;         // largest n_cols over blocks (sizes the per-warp staging buffer)
+    const int32_t *block_order; // row blocks, widest band first (longest-processing-time-first dispatch)
     uint32_t n_frames;
-    const float2 *spec;          // [n_frames][spec_stride]
-    float   *out_db;             // [n_frames][n_buckets]
-    float   *out_power;          // optional
-    float    ref_db;             // 10 * log10(0.3 * 0.3), vqt.rs:923,927
+    uint32_t n_tiles;
+    const float  *spec;        // tiled planar layout
+    float   *power;            // [n_frames][n_buckets]: |z|^2 (norm_sqr, vqt.rs:930)
 };
 
+struct DbParams {
+    const float *power;        // [n_frames][n_buckets]
+    float   *out_db;           // [n_frames][n_buckets]
+    uint32_t n_frames;
+    int32_t  n_buckets;
+    float    ref_db;           // 10 * log10(0.3 * 0.3), vqt.rs:923,927
+};
+
+constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
+constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
+
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream);
-cudaError_t launch_spmm_db(const SpmmParams &p, int frames_per_cta, cudaStream_t stream);
-cudaError_t configure_kernels(int spec_stride, int n_buckets, int *spmm_frames_per_cta);
+cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream);
+cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream);
+cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);
-size_t spmm_smem_bytes(int frames_per_cta, int spec_stride, int n_buckets);
+size_t spmm_smem_bytes(int max_cols);
 
 }  // namespace pvqt_dev

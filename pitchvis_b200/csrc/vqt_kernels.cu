@@ -1,12 +1,17 @@
 // vqt_kernels.cu -- sm_100a kernels of the VQT hot path.
 //
-//   K-fft   fft_groups_kernel   batched shared-memory Stockham real-to-complex FFT, one
-//                               launch for all window groups of all frames; replaces the
-//                               realfft `process_with_scratch` calls at vqt.rs:884-887.
-//                               Only the FFT bins the sparse kernel consumes are produced.
-//   K-spmm  spmm_db_kernel      batched complex banded SpMM over a tile of frames, with the
-//                               conjugate-part product (vqt.rs:889-910) and power_to_db
-//                               (vqt.rs:922-954) fused as the epilogue.
+//   K-fft   fft_groups_kernel    batched shared-memory Stockham real-to-complex FFT, one launch for
+//                                all window groups of all frames; replaces the realfft
+//                                `process_with_scratch` calls at vqt.rs:884-887.  Only the FFT bins
+//                                the sparse kernel consumes are produced (output-pruned last pass).
+//   K-spmm  spmm_kernel          batched complex banded SpMM, kernel coefficients stationary per
+//                                64-row block, spectra staged per 8-frame tile with cp.async;
+//                                includes the conjugate-part product (vqt.rs:889-910) and |z|^2.
+//   K-db    power_to_db_kernel   power_to_db (vqt.rs:922-954): one warp per frame, shuffle reductions.
+//
+// All complex arithmetic is issued as packed f32x2 instructions (FADD2 / FMUL2 / FFMA2, new on
+// sm_100): the FFT is issue-bound, and a complex add is one instruction instead of two, a complex
+// multiply two instead of four (profiles/r01_a_baseline_instruction_mix.txt -> r01_b).
 //
 // FFT convention (pinned by vqt.rs:1087-1128): unnormalised forward transform,
 // X[k] = sum_n x[n] exp(-2 pi i k n / N), half spectrum k = 0..N/2.
@@ -18,16 +23,18 @@ namespace pvqt_dev {
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// complex helpers
+// packed complex helpers (float2 = one 64-bit register pair)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b)
-{
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-// a * (-i)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+// a * (-i): a swap + partial negation, folded by ptxas into the consumer's operand modifiers
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+// a * w:  t = w.y * (a.y, a.x);  result = w.x * a + (-t.x, t.y)          (FMUL2 + FFMA2)
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    const float2 t = __fmul2_rn(make_float2(w.y, w.y), make_float2(a.y, a.x));
+    return __ffma2_rn(make_float2(w.x, w.x), a, make_float2(-t.x, t.y));
+}
 
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 constexpr float kCosPi8 = 0.92387953251128675613f;
@@ -39,25 +46,28 @@ __device__ __forceinline__ float2 mul_w16(float2 a)
 {
     if constexpr (M == 0) return a;
     else if constexpr (M == 1) return cmul(a, make_float2(kCosPi8, -kSinPi8));
-    else if constexpr (M == 2) return make_float2((a.x + a.y) * kSqrtHalf, (a.y - a.x) * kSqrtHalf);
+    else if constexpr (M == 2)  // ((x + y) c, (y - x) c)
+        return __fmul2_rn(__fadd2_rn(a, make_float2(a.y, -a.x)), make_float2(kSqrtHalf, kSqrtHalf));
     else if constexpr (M == 3) return cmul(a, make_float2(kSinPi8, -kCosPi8));
     else if constexpr (M == 4) return cmul_mi(a);
-    else if constexpr (M == 6) return make_float2((a.y - a.x) * kSqrtHalf, -(a.x + a.y) * kSqrtHalf);
+    else if constexpr (M == 6)  // ((y - x) c, -(x + y) c)
+        return __fmul2_rn(__fadd2_rn(make_float2(a.y, -a.x), make_float2(-a.x, -a.y)),
+                          make_float2(kSqrtHalf, kSqrtHalf));
     else if constexpr (M == 9) return cmul(a, make_float2(-kCosPi8, kSinPi8));
     else { static_assert(M < 0, "unsupported W16 power"); return a; }
 }
 
 __device__ __forceinline__ void fft2(float2 &a0, float2 &a1)
 {
-    float2 t = a0;
+    const float2 t = a0;
     a0 = cadd(t, a1);
     a1 = csub(t, a1);
 }
 
-// 4-point forward DFT, natural order in and out
+// 4-point forward DFT, natural order in and out: 8 packed adds
 __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
 {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmul_mi(csub(a1, a3));
     a0 = cadd(t0, t2);
     a1 = cadd(t1, t3);
     a2 = csub(t0, t2);
@@ -134,41 +144,78 @@ __host__ __device__ constexpr int plan_radix(int nc, int pass)
     }
 }
 
-// shared-memory index padding: one float2 of padding per 16 keeps every pass conflict-free
+// shared-memory index padding: one float2 of padding per 16 keeps every pass conflict-free.
+// pad_index(i + m) == pad_index(i) + m + m / 16 whenever m is a multiple of 16, which turns the
+// per-point index arithmetic of a pass into compile-time offsets from one base pointer.
 __host__ __device__ constexpr int pad_index(int i) { return i + (i >> 4); }
+
+// Barrier among the T threads that share one FFT (several FFTs share a CTA when T < BLOCK).
+template <int T, int BLOCK>
+__device__ __forceinline__ void fft_sync(int fid)
+{
+    if constexpr (T >= BLOCK || T < 32) __syncthreads();
+    else if constexpr (T == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(fid + 1), "n"(T) : "memory");
+}
 
 // One Stockham pass (decimation in time, autosort):
 //   butterfly b (< NC/R), k = b mod NS:
 //     v[r]  = in[b + r NC/R] * exp(-2 pi i r k / (NS R))
 //     out[(b - k) R + k + r NS] = DFT_R(v)[r]
-template <int NC, int PASS, int NS>
-__device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2 *s, int t, const float *x,
+template <int NC, int PASS, int NS, int BLOCK>
+__device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2 *s, int t, int fid, const float *x,
                                            bool valid, const FftGroup &g)
 {
     constexpr int R = plan_radix(NC, PASS);
     constexpr int T = NC / kPointsPerThread;
     constexpr int NB = kPointsPerThread / R;
+    constexpr int LD = NC / R;  // distance between the R inputs of a butterfly
     constexpr bool kFirst = PASS == 0;
     constexpr bool kLast = NS * R == NC;
+    constexpr bool kLdConst = (LD % 16) == 0;
+    constexpr bool kStConst = (NS % 16) == 0 || (NS == 1 && R == 16);
+
+    // Last pass: butterfly b produces bins b + q NS.  The split step reads Z[c] and Z[NC - c] for
+    // c in [col_lo, col_hi] only; butterflies none of whose outputs are read are skipped entirely.
+    bool need[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const int b = t + i * T;
+        need[i] = !kLast || b <= g.col_hi || b + (R - 1) * NS >= NC - g.col_hi;
+    }
 
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const int b = t + i * T;
+        if constexpr (kFirst) {
+            // z[m] = x[2m] + i x[2m+1]: the real window packed as N/2 complex points
+            const float *xb = x + 2 * b;
+            if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {  // even window start: one 8-byte load per point
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int m = b + r * (NC / R);
-            if constexpr (kFirst) {
-                // z[m] = x[2m] + i x[2m+1]: the real window packed as N/2 complex points
-                v[i * R + r] = valid ? make_float2(__ldg(x + 2 * m), __ldg(x + 2 * m + 1)) : make_float2(0.f, 0.f);
+                for (int r = 0; r < R; ++r)
+                    v[i * R + r] = valid ? __ldg(reinterpret_cast<const float2 *>(xb) + r * LD) : make_float2(0.f, 0.f);
             } else {
-                v[i * R + r] = s[pad_index(m)];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    v[i * R + r] = valid ? make_float2(__ldg(xb + 2 * r * LD), __ldg(xb + 2 * r * LD + 1))
+                                         : make_float2(0.f, 0.f);
+            }
+        } else if (need[i]) {
+            if constexpr (kLdConst) {
+                const float2 *p = s + pad_index(b);
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[i * R + r] = p[r * (LD + LD / 16)];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[i * R + r] = s[pad_index(b + r * LD)];
             }
         }
     }
-    if constexpr (!kFirst) __syncthreads();  // all reads done before the in-place overwrite
+    if constexpr (!kFirst) fft_sync<T, BLOCK>(fid);  // all reads done before the in-place overwrite
 
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
+        if (!need[i]) continue;
         const int b = t + i * T;
         if constexpr (NS > 1) {
             const int k = b & (NS - 1);
@@ -177,27 +224,35 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             for (int r = 1; r < R; ++r) v[i * R + r] = cmul(v[i * R + r], __ldg(tw + (r - 1) * NS));
         }
         butterfly<R>(&v[i * R]);
-    }
 
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const int b = t + i * T;
         const int k = b & (NS - 1);
         const int j0 = (b - k) * R + k;
+        if constexpr (kStConst) {
+            float2 *p = s + pad_index(j0);
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int o = j0 + out_index<R>(j) * NS;
-            if constexpr (kLast) {
-                // only the bins the split step reads: Z[c] and Z[NC - c], c in [col_lo, col_hi]
-                if (o <= g.col_hi || o >= NC - g.col_hi) s[pad_index(o)] = v[i * R + j];
-            } else {
-                s[pad_index(o)] = v[i * R + j];
+            for (int j = 0; j < R; ++j) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int q = out_index<R>(j);
+                const int off = NS == 1 ? q : q * (NS + NS / 16);
+                if constexpr (kLast) {
+                    const int o = j0 + q * NS;
+                    if (o <= g.col_hi || o >= NC - g.col_hi) p[off] = v[i * R + j];
+                } else {
+                    p[off] = v[i * R + j];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int o = j0 + out_index<R>(j) * NS;
+                if (!kLast || o <= g.col_hi || o >= NC - g.col_hi) s[pad_index(o)] = v[i * R + j];
             }
         }
     }
-    __syncthreads();
+    fft_sync<T, BLOCK>(fid);
 
-    if constexpr (!kLast) fft_passes<NC, PASS + 1, NS * R>(v, s, t, x, valid, g);
+    if constexpr (!kLast) fft_passes<NC, PASS + 1, NS * R, BLOCK>(v, s, t, fid, x, valid, g);
 }
 
 template <int NC, int BLOCK>
@@ -219,21 +274,24 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
 
     float2 *s = smem + fid * pad_index(NC);
     float2 v[kPointsPerThread];
-    fft_passes<NC, 0, 1>(v, s, t, x, valid, g);
+    fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g);
 
     // Real-FFT split: with Z = FFT_{NC}(z), E/O the spectra of the even/odd samples,
     //   X[c] = E[c] + W_N^c O[c],  E = (Z[c] + conj Z[NC-c]) / 2,  O = -i (Z[c] - conj Z[NC-c]) / 2
+    // written straight into the tiled spectrum layout the SpMM stages (spec_index()).
     if (valid) {
-        float2 *out = P.spec + (uint64_t)local_frame * P.spec_stride + g.spec_offset;
         const int n_cols = g.col_hi - g.col_lo + 1;
         for (int i = t; i < n_cols; i += T) {
             const int c = g.col_lo + i;
             const float2 zk = s[pad_index(c & (NC - 1))];
             const float2 zn = s[pad_index((NC - c) & (NC - 1))];
-            const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y - zn.y);
-            const float orr = 0.5f * (zk.y + zn.y), oi = -0.5f * (zk.x - zn.x);
+            const float2 e = __fmul2_rn(__fadd2_rn(zk, make_float2(zn.x, -zn.y)), make_float2(0.5f, 0.5f));
+            const float2 d = __fmul2_rn(__fadd2_rn(zk, make_float2(-zn.x, zn.y)), make_float2(0.5f, 0.5f));
+            const float2 o = cmul_mi(d);
             const float2 w = __ldg(g.split_twiddle + i);
-            out[i] = make_float2(er + (orr * w.x - oi * w.y), ei + (orr * w.y + oi * w.x));
+            const float2 xc = cadd(e, cmul(o, w));
+            P.spec[spec_index_re(local_frame, g.spec_offset + i, P.spec_stride)] = xc.x;
+            P.spec[spec_index_im(local_frame, g.spec_offset + i, P.spec_stride)] = xc.y;
         }
     }
 }
@@ -268,15 +326,11 @@ __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// K-spmm: banded complex SpMM over a tile of F frames + power_to_db epilogue
+// K-spmm: banded complex SpMM, kernel-stationary
 // ------------------------------------------------------------------------------------------
-constexpr int kSpmmThreads = 256;
-constexpr float kAMin = 1e-6f * 1e-6f;  // vqt.rs:924
-constexpr float kTopDb = 60.0f;         // vqt.rs:925
-
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
-    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
 }
 __device__ __forceinline__ void cp_async_wait_all()
@@ -285,134 +339,198 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
-template <int F>
-__global__ void __launch_bounds__(kSpmmThreads) spmm_db_kernel(const __grid_constant__ SpmmParams P)
+// One kernel coefficient k applied to the 8 frames of one spectrum record.  Accumulators are planar
+// frame pairs: re[p] = (Re y_f2p, Re y_f2p+1), im[p] likewise; xr* / xi* are the record's chunks.
+//   y += k x:        re += k.re xr - k.im xi,   im += k.re xi + k.im xr          (vqt.rs:889-894)
+//   y += k conj(x):  re += k.re xr + k.im xi,   im += k.im xr - k.re xi          (vqt.rs:896-910)
+template <bool kConj>
+__device__ __forceinline__ void mac8(float2 (&re)[4], float2 (&im)[4], float kre, float kim, const float4 &xr03,
+                                     const float4 &xr47, const float4 &xi03, const float4 &xi47)
 {
-    extern __shared__ __align__(16) unsigned char spmm_smem_raw[];
-    const int S = P.spec_stride;
-    const int NB = P.n_buckets;
-    float2 *tile = reinterpret_cast<float2 *>(spmm_smem_raw);            // [F][S]
-    float *ls = reinterpret_cast<float *>(tile + (size_t)F * S);         // [F][NB]
-    float *red = ls + (size_t)F * NB;                                    // [2][F][warps]
-    constexpr int kWarps = kSpmmThreads / 32;
+    const float2 xr[4] = {make_float2(xr03.x, xr03.y), make_float2(xr03.z, xr03.w), make_float2(xr47.x, xr47.y),
+                          make_float2(xr47.z, xr47.w)};
+    const float2 xi[4] = {make_float2(xi03.x, xi03.y), make_float2(xi03.z, xi03.w), make_float2(xi47.x, xi47.y),
+                          make_float2(xi47.z, xi47.w)};
+    const float s_im_xi = kConj ? kim : -kim;   // coefficient of xi in re
+    const float s_re_xi = kConj ? -kre : kre;   // coefficient of xi in im
+    const float2 a = make_float2(kre, kre), b = make_float2(s_im_xi, s_im_xi), c = make_float2(s_re_xi, s_re_xi),
+                 d = make_float2(kim, kim);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        re[p] = __ffma2_rn(a, xr[p], re[p]);
+        re[p] = __ffma2_rn(b, xi[p], re[p]);
+        im[p] = __ffma2_rn(c, xi[p], im[p]);
+        im[p] = __ffma2_rn(d, xr[p], im[p]);
+    }
+}
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t frame0 = blockIdx.x * F;
-    const int n_valid = min((uint32_t)F, P.n_frames - frame0);
+// Grid: (row block, group of kSpmmWarps tiles), widest row blocks first.  Each warp owns one 8-frame
+// tile: it stages the columns its block reads (contiguous 64-byte records of the tiled spectrum) with
+// cp.async, then walks the block's band; lane l accumulates rows first_row + 2l and + 2l + 1 for the
+// 8 frames.  No block-level barrier: staging buffers are warp-private.
+__global__ void __launch_bounds__(kSpmmWarps * 32) spmm_kernel(const __grid_constant__ SpmmParams P)
+{
+    extern __shared__ __align__(16) float4 spmm_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile_groups = (P.n_tiles + kSpmmWarps - 1) / kSpmmWarps;
+    const int rb = __ldg(P.block_order + blockIdx.x / tile_groups);
+    const uint32_t tile = (blockIdx.x % tile_groups) * kSpmmWarps + warp;
+    if (tile >= P.n_tiles) return;
+    const SpmmRowBlock B = P.blocks[rb];
 
-    // stage the spectra of this tile's frames (contiguous in global memory)
+    float4 *buf = spmm_smem + (size_t)warp * P.max_cols * 4;
     {
-        const float4 *src = reinterpret_cast<const float4 *>(P.spec + (size_t)frame0 * S);
-        float4 *dst = reinterpret_cast<float4 *>(tile);
-        const int n16_valid = n_valid * S / 2, n16 = F * S / 2;
-        for (int i = tid; i < n16_valid; i += kSpmmThreads) cp_async16(dst + i, src + i);
-        for (int i = n16_valid + tid; i < n16; i += kSpmmThreads) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cp_async_wait_all();
+        const float4 *src = reinterpret_cast<const float4 *>(P.spec) + ((size_t)tile * P.spec_stride + B.col_lo) * 4;
+        const int n16 = B.n_cols * 4;
+        for (int i = lane; i < n16; i += 32) cp_async16(buf + i, src + i);
     }
-    __syncthreads();
+    const int4 meta = __ldg(P.lane_meta + rb * 32 + lane);
+    const float4 *kv = P.values + (size_t)B.val_base * 32 + lane;
+    const float4 *nv = P.values + (size_t)B.nval_base * 32 + lane;
+    cp_async_wait_all();
+    __syncwarp();
 
-    float run_max[F], run_min[F];
+    float2 re0[4], im0[4], re1[4], im1[4];
 #pragma unroll
-    for (int f = 0; f < F; ++f) { run_max[f] = -CUDART_INF_F; run_min[f] = CUDART_INF_F; }
+    for (int p = 0; p < 4; ++p) re0[p] = im0[p] = re1[p] = im1[p] = make_float2(0.f, 0.f);
 
-    for (int blk = warp; blk < P.n_blocks; blk += kWarps) {
-        const SpmmBlock B = P.blocks[blk];
-        const int row = blk * kSpmmRowsPerBlock + lane;
-        const int2 rc = __ldg(P.row_cols + row);
-        float2 acc[F];
+    // Band widths are padded to multiples of kSpmmUnroll with zero coefficients and `values` has
+    // kSpmmUnroll spare slots at its end, so the next group's coefficients are always fetched
+    // unconditionally one full group ahead (they come from L2: the staging buffers leave little L1).
+    // Lanes whose pair band is shorter than the block's skip the spectrum loads (x = 0).
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 kq[kSpmmUnroll];
 #pragma unroll
-        for (int f = 0; f < F; ++f) acc[f] = make_float2(0.f, 0.f);
-
-        // y[r] += sum_c K[r,c] X[c]                                       (vqt.rs:889-894)
-        const float2 *kv = P.values + (size_t)B.val_base * kSpmmRowsPerBlock + lane;
-        for (int j = 0; j < B.width; ++j) {
-            const float2 k = __ldg(kv + j * kSpmmRowsPerBlock);
-            const int c = min(rc.x + j, S - 1);
+    for (int u = 0; u < kSpmmUnroll; ++u) kq[u] = __ldg(kv + u * 32);
+    for (int j0 = 0; j0 < B.width; j0 += kSpmmUnroll) {
+        float4 kc[kSpmmUnroll];
 #pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const float2 x = tile[f * S + c];
-                acc[f].x = fmaf(k.x, x.x, acc[f].x);
-                acc[f].x = fmaf(-k.y, x.y, acc[f].x);
-                acc[f].y = fmaf(k.x, x.y, acc[f].y);
-                acc[f].y = fmaf(k.y, x.x, acc[f].y);
-            }
+        for (int u = 0; u < kSpmmUnroll; ++u) {
+            kc[u] = kq[u];
+            kq[u] = __ldg(kv + (j0 + kSpmmUnroll + u) * 32);
         }
-        // y[r] += conj(sum_c Kneg[r,c] X[c]) = sum_c conj(Kneg[r,c]) conj(X[c])   (vqt.rs:896-910)
-        const float2 *nv = P.values + (size_t)B.nval_base * kSpmmRowsPerBlock + lane;
-        for (int j = 0; j < B.nwidth; ++j) {
-            const float2 k = __ldg(nv + j * kSpmmRowsPerBlock);  // stored already conjugated
-            const int c = min(rc.y + j, S - 1);
 #pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const float2 x = tile[f * S + c];
-                acc[f].x = fmaf(k.x, x.x, acc[f].x);
-                acc[f].x = fmaf(k.y, x.y, acc[f].x);
-                acc[f].y = fmaf(k.y, x.x, acc[f].y);
-                acc[f].y = fmaf(-k.x, x.y, acc[f].y);
+        for (int u = 0; u < kSpmmUnroll; ++u) {
+            const int j = j0 + u;
+            const int c = meta.x + j;
+            const float4 *rec = buf + c * 4;
+            const int sw = (c >> 1) & 3;  // col_lo is a multiple of 8: local and global swizzle agree
+            float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
+            if (j < meta.y) {
+                xr03 = rec[sw];
+                xr47 = rec[1 ^ sw];
+                xi03 = rec[2 ^ sw];
+                xi47 = rec[3 ^ sw];
             }
-        }
-
-        if (row < NB) {
-#pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const float p = acc[f].x * acc[f].x + acc[f].y * acc[f].y;       // norm_sqr, vqt.rs:930
-                if (P.out_power != nullptr && f < n_valid)
-                    P.out_power[(size_t)(frame0 + f) * NB + row] = p;
-                const float l = 10.0f * log10f(fmaxf(p, kAMin)) - P.ref_db;      // vqt.rs:930
-                ls[f * NB + row] = l;
-                run_max[f] = fmaxf(run_max[f], l);
-                run_min[f] = fminf(run_min[f], l);
-            }
+            mac8<false>(re0, im0, kc[u].x, kc[u].y, xr03, xr47, xi03, xi47);
+            mac8<false>(re1, im1, kc[u].z, kc[u].w, xr03, xr47, xi03, xi47);
         }
     }
+    for (int j = 0; j < B.nwidth; ++j) {
+        const float4 k = __ldg(nv + j * 32);  // conj(Kneg), see device plan
+        const int c = meta.z + j;
+        const float4 *rec = buf + c * 4;
+        const int sw = (c >> 1) & 3;
+        float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
+        if (j < meta.w) {
+            xr03 = rec[sw];
+            xr47 = rec[1 ^ sw];
+            xi03 = rec[2 ^ sw];
+            xi47 = rec[3 ^ sw];
+        }
+        mac8<true>(re0, im0, k.x, k.y, xr03, xr47, xi03, xi47);
+        mac8<true>(re1, im1, k.z, k.w, xr03, xr47, xi03, xi47);
+    }
 
-    // frame-wise max / min of the log spectrum (vqt.rs:933-938): lanes, then warps
+    // |z|^2 (norm_sqr, vqt.rs:930); lanes write adjacent row pairs -> 256-byte runs per frame
+    const int r_local = 2 * lane;
+    const uint32_t frame0 = tile * kTileFrames;
+    float *out = P.power + (size_t)frame0 * P.n_buckets + B.first_row + r_local;
+    const float pr0[kTileFrames] = {re0[0].x, re0[0].y, re0[1].x, re0[1].y, re0[2].x, re0[2].y, re0[3].x, re0[3].y};
+    const float pi0[kTileFrames] = {im0[0].x, im0[0].y, im0[1].x, im0[1].y, im0[2].x, im0[2].y, im0[3].x, im0[3].y};
+    const float pr1[kTileFrames] = {re1[0].x, re1[0].y, re1[1].x, re1[1].y, re1[2].x, re1[2].y, re1[3].x, re1[3].y};
+    const float pi1[kTileFrames] = {im1[0].x, im1[0].y, im1[1].x, im1[1].y, im1[2].x, im1[2].y, im1[3].x, im1[3].y};
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-        float mx = run_max[f], mn = run_min[f];
+    for (int f = 0; f < kTileFrames; ++f) {
+        if (frame0 + f < P.n_frames) {
+            if (r_local < B.n_rows) out[(size_t)f * P.n_buckets] = pr0[f] * pr0[f] + pi0[f] * pi0[f];
+            if (r_local + 1 < B.n_rows) out[(size_t)f * P.n_buckets + 1] = pr1[f] * pr1[f] + pi1[f] * pi1[f];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-db: power_to_db, one warp per frame
+// ------------------------------------------------------------------------------------------
+constexpr int kDbWarps = 8;
+constexpr int kDbMaxPerLane = 8;        // register-resident path: n_buckets <= 32 * 4 * 8 = 1024
+constexpr float kAMin = 1e-6f * 1e-6f;  // vqt.rs:924
+constexpr float kTopDb = 60.0f;         // vqt.rs:925
+
+__device__ __forceinline__ float log_spec(float p, float ref_db)
+{
+    return 10.0f * log10f(fmaxf(p, kAMin)) - ref_db;  // vqt.rs:930
+}
+
+__device__ __forceinline__ float db_out(float l, float floor_db, float log_spec_min)
+{
+    const float clamped = fmaxf(l, floor_db);          // vqt.rs:945-950
+    return log_spec_min > 0.0f ? clamped - log_spec_min : fmaxf(clamped, 0.0f);
+}
+
+// kVec: n_buckets % 4 == 0 and <= 1024 -> every lane keeps its float4s in registers (one pass over memory)
+template <bool kVec>
+__global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid_constant__ DbParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t frame = blockIdx.x * kDbWarps + (threadIdx.x >> 5);
+    if (frame >= P.n_frames) return;
+    const float *p = P.power + (size_t)frame * P.n_buckets;
+    float *out = P.out_db + (size_t)frame * P.n_buckets;
+    float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+
+    if constexpr (kVec) {
+        const int n4 = P.n_buckets >> 2;
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        float4 l[kDbMaxPerLane];
+#pragma unroll
+        for (int i = 0; i < kDbMaxPerLane; ++i)
+            l[i] = (lane + 32 * i < n4) ? p4[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < kDbMaxPerLane; ++i) {
+            if (lane + 32 * i < n4) {
+                l[i] = make_float4(log_spec(l[i].x, P.ref_db), log_spec(l[i].y, P.ref_db), log_spec(l[i].z, P.ref_db),
+                                   log_spec(l[i].w, P.ref_db));
+                mx = fmaxf(mx, fmaxf(fmaxf(l[i].x, l[i].y), fmaxf(l[i].z, l[i].w)));
+                mn = fminf(mn, fminf(fminf(l[i].x, l[i].y), fminf(l[i].z, l[i].w)));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // frame-wise max / min (vqt.rs:933-938)
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        const float floor_db = mx - kTopDb, log_spec_min = fmaxf(mn, floor_db);  // vqt.rs:939-940
+        float4 *o4 = reinterpret_cast<float4 *>(out);
+#pragma unroll
+        for (int i = 0; i < kDbMaxPerLane; ++i)
+            if (lane + 32 * i < n4)
+                o4[lane + 32 * i] = make_float4(db_out(l[i].x, floor_db, log_spec_min), db_out(l[i].y, floor_db, log_spec_min),
+                                                db_out(l[i].z, floor_db, log_spec_min), db_out(l[i].w, floor_db, log_spec_min));
+    } else {
+        for (int r = lane; r < P.n_buckets; r += 32) {
+            const float l = log_spec(p[r], P.ref_db);
+            mx = fmaxf(mx, l);
+            mn = fminf(mn, l);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         }
-        if (lane == 0) {
-            red[f * kWarps + warp] = mx;
-            red[(F + f) * kWarps + warp] = mn;
-        }
+        const float floor_db = mx - kTopDb, log_spec_min = fmaxf(mn, floor_db);
+        for (int r = lane; r < P.n_buckets; r += 32) out[r] = db_out(log_spec(p[r], P.ref_db), floor_db, log_spec_min);
     }
-    __syncthreads();
-
-    // clamp to 60 dB below the frame maximum and shift (vqt.rs:939-951)
-    for (int f = 0; f < n_valid; ++f) {
-        float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            mx = fmaxf(mx, red[f * kWarps + w]);
-            mn = fminf(mn, red[(F + f) * kWarps + w]);
-        }
-        const float floor_db = mx - kTopDb;
-        const float log_spec_min = fmaxf(mn, floor_db);
-        float *out = P.out_db + (size_t)(frame0 + f) * NB;
-        for (int r = tid; r < NB; r += kSpmmThreads) {
-            const float clamped = fmaxf(ls[f * NB + r], floor_db);
-            out[r] = log_spec_min > 0.0f ? clamped - log_spec_min : fmaxf(clamped, 0.0f);
-        }
-    }
-}
-
-template <int F>
-cudaError_t launch_spmm_t(const SpmmParams &p, cudaStream_t stream)
-{
-    const size_t smem = spmm_smem_bytes(F, p.spec_stride, p.n_buckets);
-    const unsigned grid = (p.n_frames + F - 1) / F;
-    spmm_db_kernel<F><<<grid, kSpmmThreads, smem, stream>>>(p);
-    return cudaGetLastError();
-}
-
-template <int F>
-cudaError_t configure_spmm_t(size_t smem)
-{
-    return cudaFuncSetAttribute(spmm_db_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 }  // namespace
@@ -423,13 +541,9 @@ size_t fft_smem_bytes(int block_threads)
     return sizeof(float2) * (size_t)pad_index(block_threads * kPointsPerThread);
 }
 
-size_t spmm_smem_bytes(int frames_per_cta, int spec_stride, int n_buckets)
-{
-    return (size_t)frames_per_cta * spec_stride * sizeof(float2) + (size_t)frames_per_cta * n_buckets * sizeof(float) +
-           2u * frames_per_cta * (kSpmmThreads / 32) * sizeof(float);
-}
+size_t spmm_smem_bytes(int max_cols) { return (size_t)kSpmmWarps * max_cols * kTileFrames * sizeof(float2); }
 
-cudaError_t configure_kernels(int spec_stride, int n_buckets, int *spmm_frames_per_cta)
+cudaError_t configure_kernels(int max_cols)
 {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(fft_groups_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -438,24 +552,9 @@ cudaError_t configure_kernels(int spec_stride, int n_buckets, int *spmm_frames_p
                                   (int)fft_smem_bytes(512))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_groups_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fft_smem_bytes(1024))) != cudaSuccess) return e;
-    // largest frame tile whose shared memory still lets two CTAs share an SM (or fits at all)
-    const size_t kTwoPerSm = 110 * 1024, kMax = 227 * 1024;
-    int f = 0;
-    for (int cand : {8, 4, 2, 1})
-        if (spmm_smem_bytes(cand, spec_stride, n_buckets) <= kTwoPerSm) { f = cand; break; }
-    if (f == 0)
-        for (int cand : {8, 4, 2, 1})
-            if (spmm_smem_bytes(cand, spec_stride, n_buckets) <= kMax) { f = cand; break; }
-    if (f == 0) return cudaErrorInvalidConfiguration;
-    const size_t smem = spmm_smem_bytes(f, spec_stride, n_buckets);
-    switch (f) {
-    case 8: e = configure_spmm_t<8>(smem); break;
-    case 4: e = configure_spmm_t<4>(smem); break;
-    case 2: e = configure_spmm_t<2>(smem); break;
-    default: e = configure_spmm_t<1>(smem); break;
-    }
-    *spmm_frames_per_cta = f;
-    return e;
+    if (spmm_smem_bytes(max_cols) > 227 * 1024) return cudaErrorInvalidConfiguration;
+    return cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)spmm_smem_bytes(max_cols));
 }
 
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream)
@@ -470,15 +569,21 @@ cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cu
     return cudaGetLastError();
 }
 
-cudaError_t launch_spmm_db(const SpmmParams &p, int frames_per_cta, cudaStream_t stream)
+cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream)
 {
-    switch (frames_per_cta) {
-    case 8: return launch_spmm_t<8>(p, stream);
-    case 4: return launch_spmm_t<4>(p, stream);
-    case 2: return launch_spmm_t<2>(p, stream);
-    case 1: return launch_spmm_t<1>(p, stream);
-    default: return cudaErrorInvalidConfiguration;
-    }
+    const unsigned tile_groups = (p.n_tiles + kSpmmWarps - 1) / kSpmmWarps;
+    spmm_kernel<<<tile_groups * p.n_blocks, kSpmmWarps * 32, spmm_smem_bytes(p.max_cols), stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream)
+{
+    const unsigned grid = (p.n_frames + kDbWarps - 1) / kDbWarps;
+    const bool vec = (p.n_buckets % 4) == 0 && p.n_buckets <= 32 * 4 * kDbMaxPerLane &&
+                     (reinterpret_cast<uintptr_t>(p.power) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.out_db) % 16) == 0;
+    if (vec) power_to_db_kernel<true><<<grid, kDbWarps * 32, 0, stream>>>(p);
+    else power_to_db_kernel<false><<<grid, kDbWarps * 32, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace pvqt_dev

@@ -81,24 +81,39 @@ def test_kernel_introspection_matches_oracle(vqt, oracle_default):
         assert (wg.negative_filter_bank is None) == (Kn.nnz == 0)
 
 
+def _untile_spec(tiled: np.ndarray, n_frames: int, stride: int) -> np.ndarray:
+    """[tile][column][16 floats: Re f0-3 | Re f4-7 | Im f0-3 | Im f4-7, chunks XOR-swizzled by column]
+    -> [frame][column] complex (layout documented in include/pvqt.h)"""
+    out = np.empty((n_frames, stride), np.complex64)
+    cols = np.arange(stride)
+    sw = (cols >> 1) & 3
+    for f in range(n_frames):
+        fi = f % 8
+        re = tiled[f // 8, cols, 4 * ((fi >> 2) ^ sw) + (fi & 3)]
+        im = tiled[f // 8, cols, 4 * ((2 + (fi >> 2)) ^ sw) + (fi & 3)]
+        out[f] = re + 1j * im
+    return out
+
+
 def test_fft_stage_against_numpy(vqt, chords):
     # the FFT kernel alone, on the consumed bins, against a float64 FFT (cuFFT/pocketfft = test oracle only)
-    n_frames = 5
+    n_frames = 13
     audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
     d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
     d_audio.upload(audio)
     stride = vqt.spec_stride
-    d_spec = pv.DeviceBuffer(vqt, n_frames * stride * 8)
+    n_tiles = (n_frames + 7) // 8
+    d_spec = pv.DeviceBuffer(vqt, n_tiles * stride * 8 * 8)
     pv.fft_device(vqt, d_audio, 1, 0, HOP, n_frames, d_spec)
-    spec = d_spec.download((n_frames, stride), np.complex64)
+    spec = _untile_spec(d_spec.download((n_tiles, stride, 16), np.float32), n_frames, stride)
     for g, wg in enumerate(vqt.kernel().window_groups):
         first, n_cols, off = vqt.group_columns(g)
         wb, we = wg.window
         for t in range(n_frames):
-            ref = np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))[first:first + n_cols]
+            full = np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))
+            ref = full[first:first + n_cols]
             got = spec[t, off:off + n_cols].astype(np.complex128)
-            scale = np.abs(np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))).max()
-            assert np.abs(got - ref).max() <= 2e-6 * scale, (g, t)
+            assert np.abs(got - ref).max() <= 2e-6 * np.abs(full).max(), (g, t)
 
 
 def test_batch_against_oracle(vqt, oracle_default, chords):
