@@ -9,6 +9,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -63,12 +64,14 @@ int host_plan_radix(int nc, int pass)
 struct DeviceBuffer {
     void *ptr = nullptr;
     size_t bytes = 0;
+    uint64_t generation = 0;  // bumped on every reallocation (cached CUDA graphs bake the pointer in)
     cudaError_t reserve(size_t want)
     {
         if (want <= bytes) return cudaSuccess;
         if (ptr) cudaFree(ptr);
         ptr = nullptr;
         bytes = 0;
+        ++generation;
         cudaError_t e = cudaMalloc(&ptr, want);
         if (e == cudaSuccess) bytes = want;
         return e;
@@ -91,6 +94,23 @@ struct pvqt {
     cudaStream_t s_in = nullptr, s_out = nullptr;  // host->device / device->host copies of the host entry points
     std::vector<cudaEvent_t> events;         // pipeline edges, reused across calls
     size_t staging_budget_samples = (size_t)256 << 20;  // device audio per super-batch (1 GiB)
+    // The pipelined host entry of one super-batch is captured into a CUDA graph and replayed while
+    // the caller keeps passing the same buffers and shapes (one launch instead of ~60 API calls).
+    struct HostCallKey {
+        const float *audio = nullptr; float *out = nullptr;
+        size_t n_streams = 0, stream_stride = 0, n_samples = 0, hop = 0, frames_per_stream = 0;
+        uint64_t generations = 0;
+        bool operator==(const HostCallKey &o) const
+        {
+            return audio == o.audio && out == o.out && n_streams == o.n_streams && stream_stride == o.stream_stride &&
+                   n_samples == o.n_samples && hop == o.hop && frames_per_stream == o.frames_per_stream &&
+                   generations == o.generations;
+        }
+    } graph_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_launches = 0;  // kernel launches one replay performs
+    size_t segments_per_batch = 3;  // measured best on B200 + PCIe Gen5 (scripts/pcie_probe.py): 2-4 equal, 6+ slower
+    bool use_graphs = false;  // PVQT_GRAPHS=1: replay buys nothing at 3 segments (the path is PCIe-bound), keep eager
 
     // device plan
     std::vector<void *> owned;          // device allocations freed on destroy
@@ -334,6 +354,26 @@ void prof_end(pvqt *v, cudaStream_t stream)
     cudaEventRecord(v->timed.back().b, stream);
 }
 
+// Spectrum / power scratch for up to `frames` frames of one kernel chunk.
+int reserve_scratch(pvqt *v, size_t frames, bool need_power, cudaStream_t stream)
+{
+    frames = std::min<size_t>(frames, v->chunk_frames);
+    const size_t tile_bytes = (size_t)v->fft.spec_stride * kTileFrames * 2 * sizeof(float);
+    const size_t want = ((frames + kTileFrames - 1) / kTileFrames) * tile_bytes;
+    if (want > v->spec.bytes) {
+        cudaError_t e = v->spec.reserve(want);
+        if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
+        // frames past the end of the last tile are never written: keep them finite
+        if ((e = cudaMemsetAsync(v->spec.ptr, 0, v->spec.bytes, stream)) != cudaSuccess)
+            return cuda_fail(e, "clear spectrum scratch");
+    }
+    if (need_power) {
+        cudaError_t e = v->power.reserve(frames * v->kernel.n_buckets * sizeof(float));
+        if (e != cudaSuccess) return cuda_fail(e, "allocate power scratch");
+    }
+    return PVQT_OK;
+}
+
 // Launch K-fft, K-spmm and K-db for the frames `(n_streams, frames_per_stream, hop)` describe.
 int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
                size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream)
@@ -346,18 +386,8 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     const size_t chunk_now = std::min<size_t>(total, chunk);
     const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
     if (!d_spec_out) {
-        const size_t want = ((chunk_now + kTileFrames - 1) / kTileFrames) * tile_elems * sizeof(float);
-        if (want > v->spec.bytes) {
-            cudaError_t e = v->spec.reserve(want);
-            if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
-            // frames past the end of the last tile are never written: keep them finite
-            if ((e = cudaMemsetAsync(v->spec.ptr, 0, v->spec.bytes, stream)) != cudaSuccess)
-                return cuda_fail(e, "clear spectrum scratch");
-        }
-        if (!d_power) {
-            cudaError_t e = v->power.reserve(chunk_now * nb * sizeof(float));
-            if (e != cudaSuccess) return cuda_fail(e, "allocate power scratch");
-        }
+        int rc = reserve_scratch(v, chunk_now, d_power == nullptr, stream);
+        if (rc) return rc;
     }
     for (size_t f0 = 0; f0 < total; f0 += chunk) {
         const uint32_t n = (uint32_t)std::min<size_t>(chunk, total - f0);
@@ -412,117 +442,221 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
 // own streams while segment i computes.  Every segment owns a distinct region of the device audio /
 // output buffers, so the three streams only need the event edges H2D(i) -> compute(i) -> D2H(i).
 // Work larger than the staging budget is processed in consecutive super-batches.
-int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples, size_t hop,
-             size_t frames_per_stream, float *out)
-{
-    const size_t n_fft = v->params.n_fft, nb = v->kernel.n_buckets;
-    if (n_streams == 0 || frames_per_stream == 0) return PVQT_OK;
-    if (!audio || !out) return fail(PVQT_INVALID_ARGUMENT, "null buffer");
-    if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
-    if (n_samples < n_fft || (frames_per_stream - 1) * hop + n_fft > n_samples)
-        return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
-    if (n_streams > 1 && stream_stride < n_samples)
-        return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
-    PVQT_CUDA(cudaSetDevice(v->device));
+struct HostJob {
+    const float *audio; float *out;
+    size_t n_streams, stream_stride, n_samples, hop, frames_per_stream;
+    size_t n_fft, nb, span;
+};
 
-    const size_t budget = v->staging_budget_samples;            // device audio per super-batch
-    const size_t span = (frames_per_stream - 1) * hop + n_fft;  // samples one stream needs
-    size_t ev_used = 0;
-    auto next_event = [&](cudaEvent_t *e) -> cudaError_t {
-        if (ev_used == v->events.size()) {
+struct EventPool {
+    pvqt *v;
+    size_t used = 0;
+    cudaError_t next(cudaEvent_t *e)
+    {
+        if (used == v->events.size()) {
             cudaEvent_t ne;
             cudaError_t rc = cudaEventCreateWithFlags(&ne, cudaEventDisableTiming);
             if (rc != cudaSuccess) return rc;
             v->events.push_back(ne);
         }
-        *e = v->events[ev_used++];
+        *e = v->events[used++];
         return cudaSuccess;
-    };
-    auto segment_frames = [&](size_t frames_in_batch) {
-        // ~6 segments per batch, at least 256 and at most one kernel chunk of frames each
-        return std::min<size_t>(std::max<size_t>((frames_in_batch + 5) / 6, 256), v->chunk_frames);
-    };
-    // one pipelined segment: copy in (s_in), compute (stream), copy out (s_out)
-    auto compute_and_copy_out = [&](cudaEvent_t copied, const float *d_audio, size_t ns, size_t dstride, size_t nf,
-                                    float *d_out, float *h_out) -> int {
-        PVQT_CUDA(cudaStreamWaitEvent(v->stream, copied, 0));
-        int rc = run_device(v, d_audio, ns, dstride, hop, nf, d_out, nullptr, nullptr, v->stream);
-        if (rc) return rc;
-        cudaEvent_t done;
-        PVQT_CUDA(next_event(&done));
-        PVQT_CUDA(cudaEventRecord(done, v->stream));
-        PVQT_CUDA(cudaStreamWaitEvent(v->s_out, done, 0));
-        PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
-        return PVQT_OK;
-    };
-    auto drain = [&]() -> int {
-        PVQT_CUDA(cudaStreamSynchronize(v->s_in));
-        PVQT_CUDA(cudaStreamSynchronize(v->stream));
-        PVQT_CUDA(cudaStreamSynchronize(v->s_out));
-        ev_used = 0;
-        return PVQT_OK;
-    };
+    }
+};
 
-    if (span <= budget && (n_streams > 1 || frames_per_stream <= 256)) {
-        // ---- stream-sharded: whole streams per segment -----------------------------------------------
-        const size_t dstride = (span + 3) & ~(size_t)3;
-        const size_t per_batch = std::max<size_t>(1, budget / dstride);
-        for (size_t b0 = 0; b0 < n_streams; b0 += per_batch) {
-            const size_t nbatch = std::min(per_batch, n_streams - b0);
-            PVQT_CUDA(v->d_audio.reserve(nbatch * dstride * sizeof(float)));
-            PVQT_CUDA(v->d_out.reserve(nbatch * frames_per_stream * nb * sizeof(float)));
-            float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
-            const size_t per_seg = std::max<size_t>(1, segment_frames(nbatch * frames_per_stream) / frames_per_stream);
-            for (size_t s0 = 0; s0 < nbatch; s0 += per_seg) {
-                const size_t ns = std::min(per_seg, nbatch - s0);
-                PVQT_CUDA(cudaMemcpy2DAsync(d_audio + s0 * dstride, dstride * sizeof(float),
-                                            audio + (b0 + s0) * stream_stride, stream_stride * sizeof(float),
-                                            span * sizeof(float), ns, cudaMemcpyHostToDevice, v->s_in));
-                cudaEvent_t copied;
-                PVQT_CUDA(next_event(&copied));
-                PVQT_CUDA(cudaEventRecord(copied, v->s_in));
-                int rc = compute_and_copy_out(copied, d_audio + s0 * dstride, ns, dstride, frames_per_stream,
-                                              d_out + s0 * frames_per_stream * nb,
-                                              out + (b0 + s0) * frames_per_stream * nb);
-                if (rc) return rc;
+size_t segment_frames(const pvqt *v, size_t frames_in_batch)
+{
+    // a few segments per batch (copies overlap compute), at least 256 and at most one kernel chunk of frames each
+    const size_t n = v->segments_per_batch;
+    return std::min<size_t>(std::max<size_t>((frames_in_batch + n - 1) / n, 256), v->chunk_frames);
+}
+
+// the copy streams join the compute stream's timeline (needed for graph capture, harmless otherwise)
+int fork_streams(pvqt *v, EventPool &ev)
+{
+    cudaEvent_t fork;
+    PVQT_CUDA(ev.next(&fork));
+    PVQT_CUDA(cudaEventRecord(fork, v->stream));
+    PVQT_CUDA(cudaStreamWaitEvent(v->s_in, fork, 0));
+    PVQT_CUDA(cudaStreamWaitEvent(v->s_out, fork, 0));
+    return PVQT_OK;
+}
+
+int join_streams(pvqt *v, EventPool &ev)
+{
+    for (cudaStream_t s : {v->s_in, v->s_out}) {
+        cudaEvent_t j;
+        PVQT_CUDA(ev.next(&j));
+        PVQT_CUDA(cudaEventRecord(j, s));
+        PVQT_CUDA(cudaStreamWaitEvent(v->stream, j, 0));
+    }
+    return PVQT_OK;
+}
+
+int compute_and_copy_out(pvqt *v, EventPool &ev, const HostJob &J, cudaEvent_t copied, const float *d_audio, size_t ns,
+                         size_t dstride, size_t nf, float *d_out, float *h_out)
+{
+    PVQT_CUDA(cudaStreamWaitEvent(v->stream, copied, 0));
+    int rc = run_device(v, d_audio, ns, dstride, J.hop, nf, d_out, nullptr, nullptr, v->stream);
+    if (rc) return rc;
+    cudaEvent_t done;
+    PVQT_CUDA(ev.next(&done));
+    PVQT_CUDA(cudaEventRecord(done, v->stream));
+    PVQT_CUDA(cudaStreamWaitEvent(v->s_out, done, 0));
+    PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * J.nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
+    return PVQT_OK;
+}
+
+// stream-sharded super-batch: streams [b0, b0 + nbatch), whole streams per segment
+int enqueue_stream_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t b0, size_t nbatch, size_t dstride)
+{
+    float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
+    const size_t per_seg = std::max<size_t>(1, segment_frames(v, nbatch * J.frames_per_stream) / J.frames_per_stream);
+    for (size_t s0 = 0; s0 < nbatch; s0 += per_seg) {
+        const size_t ns = std::min(per_seg, nbatch - s0);
+        PVQT_CUDA(cudaMemcpy2DAsync(d_audio + s0 * dstride, dstride * sizeof(float), J.audio + (b0 + s0) * J.stream_stride,
+                                    J.stream_stride * sizeof(float), J.span * sizeof(float), ns, cudaMemcpyHostToDevice,
+                                    v->s_in));
+        cudaEvent_t copied;
+        PVQT_CUDA(ev.next(&copied));
+        PVQT_CUDA(cudaEventRecord(copied, v->s_in));
+        int rc = compute_and_copy_out(v, ev, J, copied, d_audio + s0 * dstride, ns, dstride, J.frames_per_stream,
+                                      d_out + s0 * J.frames_per_stream * J.nb,
+                                      J.out + (b0 + s0) * J.frames_per_stream * J.nb);
+        if (rc) return rc;
+    }
+    return PVQT_OK;
+}
+
+// frame-range super-batch of stream s: frames [b0, b0 + nbatch); every sample is copied once
+int enqueue_frame_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t s, size_t b0, size_t nbatch)
+{
+    float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
+    const float *h_audio = J.audio + s * J.stream_stride + b0 * J.hop;
+    const size_t per_seg = segment_frames(v, nbatch);
+    size_t copied_samples = 0;
+    for (size_t f0 = 0; f0 < nbatch; f0 += per_seg) {
+        const size_t nf = std::min(per_seg, nbatch - f0);
+        const size_t need = (f0 + nf - 1) * J.hop + J.n_fft;  // batch-relative end of this segment's samples
+        if (need > copied_samples) {
+            PVQT_CUDA(cudaMemcpyAsync(d_audio + copied_samples, h_audio + copied_samples,
+                                      (need - copied_samples) * sizeof(float), cudaMemcpyHostToDevice, v->s_in));
+            copied_samples = need;
+        }
+        cudaEvent_t copied;
+        PVQT_CUDA(ev.next(&copied));
+        PVQT_CUDA(cudaEventRecord(copied, v->s_in));
+        int rc = compute_and_copy_out(v, ev, J, copied, d_audio + f0 * J.hop, 1, 0, nf, d_out + f0 * J.nb,
+                                      J.out + (s * J.frames_per_stream + b0 + f0) * J.nb);
+        if (rc) return rc;
+    }
+    return PVQT_OK;
+}
+
+int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples, size_t hop,
+             size_t frames_per_stream, float *out)
+{
+    HostJob J{audio, out, n_streams, stream_stride, n_samples, hop, frames_per_stream,
+              (size_t)v->params.n_fft, v->kernel.n_buckets, 0};
+    if (n_streams == 0 || frames_per_stream == 0) return PVQT_OK;
+    if (!audio || !out) return fail(PVQT_INVALID_ARGUMENT, "null buffer");
+    if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
+    if (n_samples < J.n_fft || (frames_per_stream - 1) * hop + J.n_fft > n_samples)
+        return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
+    if (n_streams > 1 && stream_stride < n_samples)
+        return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    J.span = (frames_per_stream - 1) * hop + J.n_fft;  // samples one stream needs
+
+    const size_t budget = v->staging_budget_samples;
+    const bool by_stream = J.span <= budget && (n_streams > 1 || frames_per_stream <= 256);
+    const size_t dstride = (J.span + 3) & ~(size_t)3;
+    const size_t streams_per_batch = std::max<size_t>(1, budget / dstride);
+    const size_t frames_per_batch =
+        budget > J.n_fft ? std::max<size_t>(1, (budget - J.n_fft) / std::max<size_t>(hop, 1) + 1) : 1;
+    const bool single_batch = by_stream ? n_streams <= streams_per_batch
+                                        : (n_streams == 1 && frames_per_stream <= frames_per_batch);
+    EventPool ev{v};
+
+    if (single_batch) {
+        const size_t audio_samples = by_stream ? n_streams * dstride : J.span;
+        const size_t frames = n_streams * frames_per_stream;
+        PVQT_CUDA(v->d_audio.reserve(audio_samples * sizeof(float)));
+        PVQT_CUDA(v->d_out.reserve(frames * J.nb * sizeof(float)));
+        int rc = reserve_scratch(v, frames, true, v->stream);
+        if (rc) return rc;
+        auto enqueue = [&]() -> int {
+            int r = fork_streams(v, ev);
+            if (r) return r;
+            r = by_stream ? enqueue_stream_batch(v, ev, J, 0, n_streams, dstride)
+                          : enqueue_frame_batch(v, ev, J, 0, 0, frames_per_stream);
+            if (r) return r;
+            return join_streams(v, ev);
+        };
+        pvqt::HostCallKey key;
+        key.audio = audio; key.out = out; key.n_streams = n_streams; key.stream_stride = stream_stride;
+        key.n_samples = n_samples; key.hop = hop; key.frames_per_stream = frames_per_stream;
+        key.generations = v->d_audio.generation * 1000003u + v->d_out.generation * 10007u + v->spec.generation * 101u +
+                          v->power.generation;
+        if (v->use_graphs && !v->profiling) {
+            if (!(v->graph_exec && key == v->graph_key)) {
+                if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                const uint64_t launches_before = v->launches.load();
+                PVQT_CUDA(cudaStreamBeginCapture(v->stream, cudaStreamCaptureModeThreadLocal));
+                rc = enqueue();
+                v->graph_launches = v->launches.load() - launches_before;
+                v->launches.store(launches_before);  // counted per replay below
+                cudaError_t e = cudaStreamEndCapture(v->stream, &graph);
+                if (rc == PVQT_OK && e == cudaSuccess && graph) {
+                    e = cudaGraphInstantiate(&v->graph_exec, graph, 0);
+                    if (e != cudaSuccess) v->graph_exec = nullptr;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                if (rc != PVQT_OK) { cudaGetLastError(); return rc; }
+                if (!v->graph_exec) { cudaGetLastError(); v->use_graphs = false; }  // capture unsupported: run eagerly
+                v->graph_key = key;
             }
-            int rc = drain();
+            if (v->graph_exec) {
+                PVQT_CUDA(cudaGraphLaunch(v->graph_exec, v->stream));
+                v->launches.fetch_add(v->graph_launches);
+                PVQT_CUDA(cudaStreamSynchronize(v->stream));
+                return PVQT_OK;
+            }
+        }
+        ev.used = 0;
+        rc = enqueue();
+        if (rc) return rc;
+        PVQT_CUDA(cudaStreamSynchronize(v->stream));
+        return PVQT_OK;
+    }
+
+    // several super-batches: eager, one drain per batch
+    if (by_stream) {
+        for (size_t b0 = 0; b0 < n_streams; b0 += streams_per_batch) {
+            const size_t nbatch = std::min(streams_per_batch, n_streams - b0);
+            PVQT_CUDA(v->d_audio.reserve(nbatch * dstride * sizeof(float)));
+            PVQT_CUDA(v->d_out.reserve(nbatch * frames_per_stream * J.nb * sizeof(float)));
+            ev.used = 0;
+            int rc = fork_streams(v, ev);
+            if (!rc) rc = enqueue_stream_batch(v, ev, J, b0, nbatch, dstride);
+            if (!rc) rc = join_streams(v, ev);
             if (rc) return rc;
+            PVQT_CUDA(cudaStreamSynchronize(v->stream));
         }
     } else {
-        // ---- frame-range sharded: one long recording at a time, each sample copied once ---------------
-        const size_t frames_per_batch = budget > n_fft ? std::max<size_t>(1, (budget - n_fft) / std::max<size_t>(hop, 1) + 1)
-                                                       : 1;
-        for (size_t s = 0; s < n_streams; ++s) {
-            const float *h_audio = audio + s * stream_stride;
+        for (size_t s = 0; s < n_streams; ++s)
             for (size_t b0 = 0; b0 < frames_per_stream; b0 += frames_per_batch) {
                 const size_t nbatch = std::min(frames_per_batch, frames_per_stream - b0);
-                const size_t batch_samples = (nbatch - 1) * hop + n_fft;
-                PVQT_CUDA(v->d_audio.reserve(batch_samples * sizeof(float)));
-                PVQT_CUDA(v->d_out.reserve(nbatch * nb * sizeof(float)));
-                float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
-                const size_t per_seg = segment_frames(nbatch);
-                size_t copied_samples = 0;  // samples of this batch already on the device
-                for (size_t f0 = 0; f0 < nbatch; f0 += per_seg) {
-                    const size_t nf = std::min(per_seg, nbatch - f0);
-                    const size_t need = (f0 + nf - 1) * hop + n_fft;  // batch-relative end of this segment's samples
-                    if (need > copied_samples) {
-                        PVQT_CUDA(cudaMemcpyAsync(d_audio + copied_samples, h_audio + b0 * hop + copied_samples,
-                                                  (need - copied_samples) * sizeof(float), cudaMemcpyHostToDevice,
-                                                  v->s_in));
-                        copied_samples = need;
-                    }
-                    cudaEvent_t copied;
-                    PVQT_CUDA(next_event(&copied));
-                    PVQT_CUDA(cudaEventRecord(copied, v->s_in));
-                    int rc = compute_and_copy_out(copied, d_audio + f0 * hop, 1, 0, nf, d_out + f0 * nb,
-                                                  out + (s * frames_per_stream + b0 + f0) * nb);
-                    if (rc) return rc;
-                }
-                int rc = drain();
+                PVQT_CUDA(v->d_audio.reserve(((nbatch - 1) * hop + J.n_fft) * sizeof(float)));
+                PVQT_CUDA(v->d_out.reserve(nbatch * J.nb * sizeof(float)));
+                ev.used = 0;
+                int rc = fork_streams(v, ev);
+                if (!rc) rc = enqueue_frame_batch(v, ev, J, s, b0, nbatch);
+                if (!rc) rc = join_streams(v, ev);
                 if (rc) return rc;
+                PVQT_CUDA(cudaStreamSynchronize(v->stream));
             }
-        }
     }
     return PVQT_OK;
 }
@@ -681,6 +815,8 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
         (e = cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking)) != cudaSuccess)
         return cuda_error(e, "cudaStreamCreate");
 
+    if (const char *s = std::getenv("PVQT_SEGMENTS")) v->segments_per_batch = std::max(1, std::atoi(s));
+    if (const char *s = std::getenv("PVQT_GRAPHS")) v->use_graphs = std::atoi(s) != 0;
     pvqt *raw = v.release();
     int rc = build_device_plan(raw);
     if (rc != PVQT_OK) {
@@ -701,6 +837,7 @@ void pvqt_destroy(pvqt *v)
     for (cudaStream_t s : {v->s_in, v->stream, v->s_out})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (cudaEvent_t e : v->events) cudaEventDestroy(e);
+    if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
     for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (void *p : v->owned) cudaFree(p);
     v->spec.release();

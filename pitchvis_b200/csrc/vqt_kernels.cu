@@ -22,6 +22,13 @@
 namespace pvqt_dev {
 namespace {
 
+// Programmatic dependent launch: K-spmm and K-db are launched with the programmatic-stream-
+// serialization attribute, so their CTAs may become resident while the producer kernel drains.
+// pdl_wait() blocks until the producer grid has completed and its writes are visible;
+// pdl_launch_dependents() lets the next kernel in the stream start its prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" :::); }
+
 // ------------------------------------------------------------------------------------------
 // packed complex helpers (float2 = one 64-bit register pair)
 // ------------------------------------------------------------------------------------------
@@ -300,6 +307,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant__ FftParams P)
 {
     extern __shared__ __align__(16) float2 fft_smem[];
+    pdl_launch_dependents();
     int gi = 0;
 #pragma unroll 1
     while (gi + 1 < P.n_groups && (int)blockIdx.x >= P.group[gi + 1].cta_begin) ++gi;
@@ -379,14 +387,23 @@ __global__ void __launch_bounds__(kSpmmWarps * 32) spmm_kernel(const __grid_cons
     const SpmmRowBlock B = P.blocks[rb];
 
     float4 *buf = spmm_smem + (size_t)warp * P.max_cols * 4;
+    const int4 meta = __ldg(P.lane_meta + rb * 32 + lane);
+    const float4 *kv = P.values + (size_t)B.val_base * 32 + lane;
+    const float4 *nv = P.values + (size_t)B.nval_base * 32 + lane;
+    // Band widths are padded to multiples of kSpmmUnroll with zero coefficients and `values` has
+    // kSpmmUnroll spare slots at its end, so the next group's coefficients are always fetched
+    // unconditionally one full group ahead (they come from L2: the staging buffers leave little L1).
+    float4 kq[kSpmmUnroll];
+#pragma unroll
+    for (int u = 0; u < kSpmmUnroll; ++u) kq[u] = __ldg(kv + u * 32);
+
+    pdl_launch_dependents();
+    pdl_wait();  // everything above is plan data; the spectra below come from K-fft
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.spec) + ((size_t)tile * P.spec_stride + B.col_lo) * 4;
         const int n16 = B.n_cols * 4;
         for (int i = lane; i < n16; i += 32) cp_async16(buf + i, src + i);
     }
-    const int4 meta = __ldg(P.lane_meta + rb * 32 + lane);
-    const float4 *kv = P.values + (size_t)B.val_base * 32 + lane;
-    const float4 *nv = P.values + (size_t)B.nval_base * 32 + lane;
     cp_async_wait_all();
     __syncwarp();
 
@@ -394,14 +411,8 @@ __global__ void __launch_bounds__(kSpmmWarps * 32) spmm_kernel(const __grid_cons
 #pragma unroll
     for (int p = 0; p < 4; ++p) re0[p] = im0[p] = re1[p] = im1[p] = make_float2(0.f, 0.f);
 
-    // Band widths are padded to multiples of kSpmmUnroll with zero coefficients and `values` has
-    // kSpmmUnroll spare slots at its end, so the next group's coefficients are always fetched
-    // unconditionally one full group ahead (they come from L2: the staging buffers leave little L1).
     // Lanes whose pair band is shorter than the block's skip the spectrum loads (x = 0).
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 kq[kSpmmUnroll];
-#pragma unroll
-    for (int u = 0; u < kSpmmUnroll; ++u) kq[u] = __ldg(kv + u * 32);
     for (int j0 = 0; j0 < B.width; j0 += kSpmmUnroll) {
         float4 kc[kSpmmUnroll];
 #pragma unroll
@@ -484,6 +495,8 @@ __global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid
 {
     const int lane = threadIdx.x & 31;
     const uint32_t frame = blockIdx.x * kDbWarps + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    pdl_wait();  // P.power is written by K-spmm
     if (frame >= P.n_frames) return;
     const float *p = P.power + (size_t)frame * P.n_buckets;
     float *out = P.out_db + (size_t)frame * P.n_buckets;
@@ -569,11 +582,29 @@ cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cu
     return cudaGetLastError();
 }
 
+namespace {
+template <typename Kernel, typename Params>
+cudaError_t launch_dependent(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                             const Params &p)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+}  // namespace
+
 cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream)
 {
     const unsigned tile_groups = (p.n_tiles + kSpmmWarps - 1) / kSpmmWarps;
-    spmm_kernel<<<tile_groups * p.n_blocks, kSpmmWarps * 32, spmm_smem_bytes(p.max_cols), stream>>>(p);
-    return cudaGetLastError();
+    return launch_dependent(spmm_kernel, tile_groups * p.n_blocks, kSpmmWarps * 32, spmm_smem_bytes(p.max_cols), stream, p);
 }
 
 cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream)
@@ -581,9 +612,8 @@ cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream)
     const unsigned grid = (p.n_frames + kDbWarps - 1) / kDbWarps;
     const bool vec = (p.n_buckets % 4) == 0 && p.n_buckets <= 32 * 4 * kDbMaxPerLane &&
                      (reinterpret_cast<uintptr_t>(p.power) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.out_db) % 16) == 0;
-    if (vec) power_to_db_kernel<true><<<grid, kDbWarps * 32, 0, stream>>>(p);
-    else power_to_db_kernel<false><<<grid, kDbWarps * 32, 0, stream>>>(p);
-    return cudaGetLastError();
+    return vec ? launch_dependent(power_to_db_kernel<true>, grid, kDbWarps * 32, 0, stream, p)
+               : launch_dependent(power_to_db_kernel<false>, grid, kDbWarps * 32, 0, stream, p);
 }
 
 }  // namespace pvqt_dev
