@@ -256,3 +256,138 @@ def test_create_sines(params: OrcParams, freqs, t_diff: float = 0.0) -> np.ndarr
 
 
 test_create_sines.__test__ = False  # not a pytest test
+
+
+# ---------------------------------------------------------------------------------------------------
+# analysis oracle (oracle/analysis_oracle.c)
+# ---------------------------------------------------------------------------------------------------
+class OrcPeakParams(C.Structure):
+    _fields_ = [("min_prominence", C.c_float), ("min_height", C.c_float)]
+
+
+class OrcAnalysisParams(C.Structure):
+    _fields_ = [
+        ("spectrogram_length", C.c_uint64),
+        ("peak_config", OrcPeakParams),
+        ("bassline_peak_config", OrcPeakParams),
+        ("highest_bassnote", C.c_uint64),
+        ("vqt_smoothing_duration_base_ns", C.c_uint64),
+        ("vqt_smoothing_calmness_min", C.c_float),
+        ("vqt_smoothing_calmness_max", C.c_float),
+        ("note_calmness_smoothing_duration_ns", C.c_uint64),
+        ("scene_calmness_smoothing_duration_ns", C.c_uint64),
+        ("tuning_inaccuracy_smoothing_duration_ns", C.c_uint64),
+        ("harmonic_threshold", C.c_float),
+    ]
+
+
+class OrcContinuousPeak(C.Structure):
+    _fields_ = [("center", C.c_float), ("size", C.c_float)]
+
+
+_alib = None
+
+
+def alib() -> C.CDLL:
+    global _alib
+    if _alib is not None:
+        return _alib
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    u32p = C.POINTER(C.c_uint32)
+    L.orc_analysis_default_params.argtypes = [C.POINTER(OrcAnalysisParams)]
+    L.orc_analysis_default_params.restype = None
+    L.orc_analysis_new.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.POINTER(OrcAnalysisParams)]
+    L.orc_analysis_new.restype = C.c_void_p
+    L.orc_analysis_free.argtypes = [C.c_void_p]
+    L.orc_analysis_free.restype = None
+    L.orc_analysis_update_vqt_smoothing_duration.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    L.orc_analysis_update_vqt_smoothing_duration.restype = None
+    L.orc_analysis_preprocess.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_uint64]
+    L.orc_analysis_n_buckets.argtypes = [C.c_void_p]
+    L.orc_analysis_n_buckets.restype = C.c_size_t
+    L.orc_analysis_peaks.argtypes = [C.c_void_p, u32p, C.c_size_t]
+    L.orc_analysis_peaks.restype = C.c_size_t
+    L.orc_analysis_peaks_continuous.argtypes = [C.c_void_p, C.POINTER(OrcContinuousPeak), C.c_size_t]
+    L.orc_analysis_peaks_continuous.restype = C.c_size_t
+    L.orc_analysis_vectors.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, fp]
+    L.orc_analysis_vectors.restype = None
+    L.orc_analysis_scene_calmness.argtypes = [C.c_void_p]
+    L.orc_analysis_scene_calmness.restype = C.c_float
+    L.orc_analysis_tuning_inaccuracy.argtypes = [C.c_void_p]
+    L.orc_analysis_tuning_inaccuracy.restype = C.c_float
+    L.orc_find_peaks.argtypes = [fp, C.c_size_t, C.c_float, C.c_float, C.c_uint32, C.c_int, u32p, C.c_size_t]
+    L.orc_find_peaks.restype = C.c_size_t
+    L.orc_ema_update.argtypes = [C.c_float, C.c_int, C.c_uint64, C.c_float, C.c_uint64]
+    L.orc_ema_update.restype = C.c_float
+    _alib = L
+    return L
+
+
+def analysis_default_params() -> OrcAnalysisParams:
+    p = OrcAnalysisParams()
+    alib().orc_analysis_default_params(C.byref(p))
+    return p
+
+
+def find_peaks(x: np.ndarray, min_prominence: float, min_height: float, buckets_per_octave: int,
+               order: int = 0) -> np.ndarray:
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty(x.shape[0], np.uint32)
+    n = alib().orc_find_peaks(_fptr(x), x.shape[0], min_prominence, min_height, buckets_per_octave, order,
+                              out.ctypes.data_as(C.POINTER(C.c_uint32)), out.shape[0])
+    return out[:n].copy()
+
+
+def ema_update(y: float, horizon_ns, new_value: float, timestep_ns: int) -> float:
+    return float(alib().orc_ema_update(y, 0 if horizon_ns is None else 1, horizon_ns or 0, new_value, timestep_ns))
+
+
+class OracleAnalysisState:
+    """Mirror of pitchvis_analysis::analysis::AnalysisState on the CPU oracle."""
+
+    def __init__(self, min_freq=55.0, octaves=7, buckets_per_octave=84, params: OrcAnalysisParams | None = None):
+        self.params = params if params is not None else analysis_default_params()
+        self._h = C.c_void_p(alib().orc_analysis_new(min_freq, octaves, buckets_per_octave, C.byref(self.params)))
+        self.n = int(alib().orc_analysis_n_buckets(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            alib().orc_analysis_free(self._h)
+            self._h = C.c_void_p()
+
+    def update_vqt_smoothing_duration(self, duration_ns):
+        alib().orc_analysis_update_vqt_smoothing_duration(self._h, 0 if duration_ns is None else 1, duration_ns or 0)
+
+    def preprocess(self, x_vqt: np.ndarray, frame_time_ns: int):
+        x = np.ascontiguousarray(x_vqt, np.float32)
+        rc = alib().orc_analysis_preprocess(self._h, _fptr(x), x.shape[0], frame_time_ns)
+        if rc == ORC_BAD_LENGTH:
+            raise ValueError("x_vqt.len() must equal range.n_buckets()")
+
+    @property
+    def peaks(self) -> np.ndarray:
+        out = np.empty(self.n, np.uint32)
+        m = alib().orc_analysis_peaks(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), self.n)
+        return out[:m].copy()
+
+    @property
+    def peaks_continuous(self) -> np.ndarray:
+        arr = (OrcContinuousPeak * self.n)()
+        m = alib().orc_analysis_peaks_continuous(self._h, arr, self.n)
+        return np.array([(arr[i].center, arr[i].size) for i in range(m)], np.float32).reshape(m, 2)
+
+    def vectors(self):
+        out = [np.empty(self.n, np.float32) for _ in range(6)]
+        alib().orc_analysis_vectors(self._h, *[_fptr(o) for o in out])
+        names = ["x_vqt_smoothed", "x_vqt_peakfiltered", "x_vqt_afterglow", "calmness", "pitch_accuracy",
+                 "pitch_deviation"]
+        return dict(zip(names, out))
+
+    @property
+    def smoothed_scene_calmness(self) -> float:
+        return float(alib().orc_analysis_scene_calmness(self._h))
+
+    @property
+    def smoothed_tuning_grid_inaccuracy(self) -> float:
+        return float(alib().orc_analysis_tuning_inaccuracy(self._h))
