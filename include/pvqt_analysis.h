@@ -1,0 +1,106 @@
+/*
+ * pvqt_analysis.h -- C ABI of the AnalysisState epilogue (libpvqt.so), the optional stage after the
+ * VQT: per-bin calmness-adaptive EMA smoothing, peak detection, continuous peak refinement, bass
+ * promotion, afterglow, calmness and tuning measures.
+ *
+ * Replaces pitchvis_analysis::analysis::AnalysisState (analysis.rs:119-410) and its modules
+ * (analysis_modules/{peak_detection,calmness,afterglow,pitch_analysis}.rs, util.rs:91-137).
+ * One state object holds `n_streams` independent AnalysisStates (one per audio stream); each is a
+ * recurrence in time, so a batch call advances every stream by `n_frames` frames, streams in
+ * parallel on the GPU (one CTA per stream), frames in order.
+ *
+ * Peak semantics: the reference delegates to the crates.io crate find_peaks 0.1.5, which is not part
+ * of the reference tree; this library implements strict local maxima (plateaus at their middle),
+ * then min_height, then min_distance (taller peaks win), then min_prominence -- the algorithm of
+ * scipy.signal.find_peaks, which the crate advertises compatibility with ("peaks").
+ */
+#ifndef PVQT_ANALYSIS_H
+#define PVQT_ANALYSIS_H
+
+#include "pvqt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PeakDetectionParameters (peak_detection.rs:10-15) */
+typedef struct pvqt_peak_params {
+    float min_prominence;
+    float min_height;
+} pvqt_peak_params;
+
+/* AnalysisParameters (analysis.rs:36-65); std::time::Duration fields in nanoseconds */
+typedef struct pvqt_analysis_params {
+    uint64_t         spectrogram_length;
+    pvqt_peak_params peak_config;
+    pvqt_peak_params bassline_peak_config;
+    uint64_t         highest_bassnote;
+    uint64_t         vqt_smoothing_duration_base_ns;
+    float            vqt_smoothing_calmness_min;
+    float            vqt_smoothing_calmness_max;
+    uint64_t         note_calmness_smoothing_duration_ns;
+    uint64_t         scene_calmness_smoothing_duration_ns;
+    uint64_t         tuning_inaccuracy_smoothing_duration_ns;
+    float            harmonic_threshold;
+} pvqt_analysis_params;
+
+/* VqtRange (vqt.rs:239-255) */
+typedef struct pvqt_range {
+    float    min_freq;
+    uint32_t octaves;
+    uint32_t buckets_per_octave;
+} pvqt_range;
+
+/* ContinuousPeak (peak_detection.rs:17-23) */
+typedef struct pvqt_continuous_peak {
+    float center;
+    float size;
+} pvqt_continuous_peak;
+
+/* Per-frame results of a batch call: the public fields of AnalysisState (analysis.rs:119-177) after
+ * each preprocess().  Every pointer may be NULL (that output is skipped).  S = n_streams, T = n_frames,
+ * NB = n_buckets, P = max_peaks (peaks beyond P are counted but not stored). */
+typedef struct pvqt_analysis_outputs {
+    uint32_t              max_peaks;
+    uint32_t             *peak_count;        /* [S][T]       |peaks| */
+    uint32_t             *peak_indices;      /* [S][T][P]    peaks, ascending */
+    pvqt_continuous_peak *peaks_continuous;  /* [S][T][P]    sorted by center (peak_detection.rs:145) */
+    float                *x_vqt_smoothed;    /* [S][T][NB] */
+    float                *x_vqt_peakfiltered;/* [S][T][NB] */
+    float                *x_vqt_afterglow;   /* [S][T][NB] */
+    float                *calmness;          /* [S][T][NB] */
+    float                *pitch_accuracy;    /* [S][T][NB] */
+    float                *pitch_deviation;   /* [S][T][NB] */
+    float                *smoothed_scene_calmness;          /* [S][T] */
+    float                *smoothed_tuning_grid_inaccuracy;  /* [S][T] */
+} pvqt_analysis_outputs;
+
+typedef struct pvqt_analysis pvqt_analysis;
+
+/* `impl Default for AnalysisParameters` (analysis.rs:72-98) */
+int  pvqt_analysis_default_params(pvqt_analysis_params *out);
+/* AnalysisState::new (analysis.rs:192-241), n_streams independent states on `device` */
+int  pvqt_analysis_create(const pvqt_range *range, const pvqt_analysis_params *params, size_t n_streams, int device,
+                          pvqt_analysis **out);
+void pvqt_analysis_destroy(pvqt_analysis *a);
+size_t pvqt_analysis_n_buckets(const pvqt_analysis *a);
+size_t pvqt_analysis_n_streams(const pvqt_analysis *a);
+/* AnalysisState::update_vqt_smoothing_duration (analysis.rs:251-270); has_duration == 0 <=> None */
+int  pvqt_analysis_update_vqt_smoothing_duration(pvqt_analysis *a, int has_duration, uint64_t duration_ns);
+
+/* AnalysisState::preprocess (analysis.rs:288-404) for T consecutive frames of every stream.
+ * db: host [S][T][NB] dB spectra (the layout pvqt_calc_streams_db writes); n_buckets must equal NB
+ * (PVQT_BAD_LENGTH where the reference asserts, analysis.rs:289).  frame_time_ns: Duration per frame.
+ * `out` holds host pointers. */
+int  pvqt_analysis_preprocess_batch(pvqt_analysis *a, const float *db, size_t n_buckets, size_t n_frames,
+                                    uint64_t frame_time_ns, const pvqt_analysis_outputs *out);
+/* Same with device pointers for db and for every non-NULL member of `out` (fused after
+ * pvqt_calc_db_device on the same device); asynchronous on cuda_stream (NULL = the state's stream). */
+int  pvqt_analysis_preprocess_device(pvqt_analysis *a, const float *d_db, size_t n_buckets, size_t n_frames,
+                                     uint64_t frame_time_ns, const pvqt_analysis_outputs *d_out, void *cuda_stream);
+int  pvqt_analysis_synchronize(pvqt_analysis *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVQT_ANALYSIS_H */

@@ -10,3 +10,4 @@ from .vqt import (  # noqa: F401
     VqtParameters, VqtRange, WindowExceedsNFft, WindowGroup, calc_db_device, fft_device, filter_bank_params,
     synchronize,
 )
+from .analysis import AnalysisParameters, AnalysisState, PeakDetectionParameters  # noqa: F401,E402

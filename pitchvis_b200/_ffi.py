@@ -59,7 +59,48 @@ class PvqtCsrView(C.Structure):
     ]
 
 
-# name -> (restype, argtypes); every symbol include/pvqt.h declares
+class PvqtPeakParams(C.Structure):
+    _fields_ = [("min_prominence", C.c_float), ("min_height", C.c_float)]
+
+
+class PvqtAnalysisParams(C.Structure):
+    _fields_ = [
+        ("spectrogram_length", C.c_uint64),
+        ("peak_config", PvqtPeakParams),
+        ("bassline_peak_config", PvqtPeakParams),
+        ("highest_bassnote", C.c_uint64),
+        ("vqt_smoothing_duration_base_ns", C.c_uint64),
+        ("vqt_smoothing_calmness_min", C.c_float),
+        ("vqt_smoothing_calmness_max", C.c_float),
+        ("note_calmness_smoothing_duration_ns", C.c_uint64),
+        ("scene_calmness_smoothing_duration_ns", C.c_uint64),
+        ("tuning_inaccuracy_smoothing_duration_ns", C.c_uint64),
+        ("harmonic_threshold", C.c_float),
+    ]
+
+
+class PvqtRange(C.Structure):
+    _fields_ = [("min_freq", C.c_float), ("octaves", C.c_uint32), ("buckets_per_octave", C.c_uint32)]
+
+
+class PvqtAnalysisOutputs(C.Structure):
+    _fields_ = [
+        ("max_peaks", C.c_uint32),
+        ("peak_count", C.c_void_p),
+        ("peak_indices", C.c_void_p),
+        ("peaks_continuous", C.c_void_p),
+        ("x_vqt_smoothed", C.c_void_p),
+        ("x_vqt_peakfiltered", C.c_void_p),
+        ("x_vqt_afterglow", C.c_void_p),
+        ("calmness", C.c_void_p),
+        ("pitch_accuracy", C.c_void_p),
+        ("pitch_deviation", C.c_void_p),
+        ("smoothed_scene_calmness", C.c_void_p),
+        ("smoothed_tuning_grid_inaccuracy", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/*.h declares
 _FP = C.POINTER(C.c_float)
 _VP = C.c_void_p
 _SZ = C.c_size_t
@@ -122,6 +163,17 @@ SIGNATURES = {
     "pvqt_multi_handle": (_VP, [_VP, C.c_int]),
     "pvqt_multi_calc_batch_db": (C.c_int, [_VP, _FP, _SZ, _SZ, _SZ, _FP]),
     "pvqt_multi_calc_streams_db": (C.c_int, [_VP, _FP, _SZ, _SZ, _SZ, _SZ, _SZ, _FP]),
+    "pvqt_analysis_default_params": (C.c_int, [C.POINTER(PvqtAnalysisParams)]),
+    "pvqt_analysis_create": (C.c_int, [C.POINTER(PvqtRange), C.POINTER(PvqtAnalysisParams), _SZ, C.c_int,
+                                       C.POINTER(_VP)]),
+    "pvqt_analysis_destroy": (None, [_VP]),
+    "pvqt_analysis_n_buckets": (_SZ, [_VP]),
+    "pvqt_analysis_n_streams": (_SZ, [_VP]),
+    "pvqt_analysis_update_vqt_smoothing_duration": (C.c_int, [_VP, C.c_int, C.c_uint64]),
+    "pvqt_analysis_preprocess_batch": (C.c_int, [_VP, _FP, _SZ, _SZ, C.c_uint64, C.POINTER(PvqtAnalysisOutputs)]),
+    "pvqt_analysis_preprocess_device": (C.c_int, [_VP, _VP, _SZ, _SZ, C.c_uint64, C.POINTER(PvqtAnalysisOutputs),
+                                                  _VP]),
+    "pvqt_analysis_synchronize": (C.c_int, [_VP]),
 }
 
 _lib = None

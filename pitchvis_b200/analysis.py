@@ -1,0 +1,143 @@
+"""Host-side mirror of `pitchvis_analysis::analysis` on top of the C ABI (include/pvqt_analysis.h).
+
+`AnalysisParameters`, `PeakDetectionParameters`, `ContinuousPeak`, `AnalysisState.new/preprocess/
+update_vqt_smoothing_duration` keep the reference's names (analysis.rs:36-410).  One `AnalysisState`
+holds `n_streams` independent states; `preprocess_batch` advances all of them by T frames and returns
+the reference's public fields after every frame.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import PvqtAnalysisOutputs, PvqtAnalysisParams, PvqtPeakParams, PvqtRange
+from .vqt import PvqtRuntimeError, VqtRange
+
+MS = 1_000_000
+
+
+@dataclass
+class PeakDetectionParameters:
+    """peak_detection.rs:10-15"""
+    min_prominence: float
+    min_height: float
+
+
+@dataclass
+class AnalysisParameters:
+    """analysis.rs:36-98 (defaults = `impl Default`); durations in nanoseconds"""
+    spectrogram_length: int = 400
+    peak_config: PeakDetectionParameters = field(default_factory=lambda: PeakDetectionParameters(10.0, 4.0))
+    bassline_peak_config: PeakDetectionParameters = field(default_factory=lambda: PeakDetectionParameters(5.0, 3.5))
+    highest_bassnote: int = 12 * 2 + 4
+    vqt_smoothing_duration_base: int = 70 * MS
+    vqt_smoothing_calmness_min: float = 0.6
+    vqt_smoothing_calmness_max: float = 2.0
+    note_calmness_smoothing_duration: int = 3_500 * MS
+    scene_calmness_smoothing_duration: int = 800 * MS
+    tuning_inaccuracy_smoothing_duration: int = 4_000 * MS
+    harmonic_threshold: float = 0.3
+
+    def to_c(self) -> PvqtAnalysisParams:
+        return PvqtAnalysisParams(
+            self.spectrogram_length,
+            PvqtPeakParams(self.peak_config.min_prominence, self.peak_config.min_height),
+            PvqtPeakParams(self.bassline_peak_config.min_prominence, self.bassline_peak_config.min_height),
+            self.highest_bassnote, self.vqt_smoothing_duration_base, self.vqt_smoothing_calmness_min,
+            self.vqt_smoothing_calmness_max, self.note_calmness_smoothing_duration,
+            self.scene_calmness_smoothing_duration, self.tuning_inaccuracy_smoothing_duration,
+            self.harmonic_threshold)
+
+
+def _check(rc: int):
+    if rc == _ffi.PVQT_OK:
+        return
+    if rc == _ffi.PVQT_BAD_LENGTH:
+        raise ValueError(_ffi.last_error())  # the reference asserts (analysis.rs:289)
+    raise PvqtRuntimeError(rc, _ffi.last_error())
+
+
+VECTOR_FIELDS = ("x_vqt_smoothed", "x_vqt_peakfiltered", "x_vqt_afterglow", "calmness", "pitch_accuracy",
+                 "pitch_deviation")
+
+
+class AnalysisState:
+    """`AnalysisState` for n_streams independent audio streams on one GPU."""
+
+    def __init__(self, range: VqtRange, params: Optional[AnalysisParameters] = None, n_streams: int = 1,
+                 device: int = 0):
+        self._lib = _ffi.load()
+        self.range = range
+        self.params = params if params is not None else AnalysisParameters()
+        self.n_streams = n_streams
+        self.n_buckets = range.n_buckets()
+        self._h = C.c_void_p()
+        r = PvqtRange(range.min_freq, range.octaves, range.buckets_per_octave)
+        p = self.params.to_c()
+        _check(self._lib.pvqt_analysis_create(C.byref(r), C.byref(p), n_streams, device, C.byref(self._h)))
+
+    @classmethod
+    def new(cls, range: VqtRange, params: AnalysisParameters) -> "AnalysisState":
+        return cls(range, params)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pvqt_analysis_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_vqt_smoothing_duration(self, new_duration_ns: Optional[int]):
+        _check(self._lib.pvqt_analysis_update_vqt_smoothing_duration(
+            self._h, 0 if new_duration_ns is None else 1, new_duration_ns or 0))
+
+    def preprocess_batch(self, db: np.ndarray, frame_time_ns: int, max_peaks: int = 64,
+                         vectors: bool = True) -> Dict[str, np.ndarray]:
+        """db: [n_streams][T][n_buckets] (or [T][n_buckets] for one stream).  Returns per-frame results."""
+        db = np.ascontiguousarray(db, np.float32)
+        if db.ndim == 2:
+            db = db[None]
+        if db.ndim != 3 or db.shape[0] != self.n_streams:
+            raise ValueError("db must be [n_streams][n_frames][n_buckets]")
+        S, T, NB = db.shape
+        res = {
+            "peak_count": np.zeros((S, T), np.uint32),
+            "peak_indices": np.zeros((S, T, max_peaks), np.uint32),
+            "peaks_continuous": np.zeros((S, T, max_peaks, 2), np.float32),
+            "smoothed_scene_calmness": np.zeros((S, T), np.float32),
+            "smoothed_tuning_grid_inaccuracy": np.zeros((S, T), np.float32),
+        }
+        if vectors:
+            for name in VECTOR_FIELDS:
+                res[name] = np.zeros((S, T, NB), np.float32)
+        out = PvqtAnalysisOutputs()
+        out.max_peaks = max_peaks
+        for name, arr in res.items():
+            setattr(out, name, arr.ctypes.data_as(C.c_void_p))
+        _check(self._lib.pvqt_analysis_preprocess_batch(
+            self._h, db.ctypes.data_as(C.POINTER(C.c_float)), NB, T, frame_time_ns, C.byref(out)))
+        return res
+
+    def preprocess(self, x_vqt, frame_time_ns: int) -> Dict[str, np.ndarray]:
+        """`AnalysisState::preprocess` for one frame of a single-stream state."""
+        x = np.ascontiguousarray(x_vqt, np.float32)
+        if x.ndim != 1:
+            raise ValueError("x_vqt must be one frame")
+        if self.n_streams != 1:
+            raise ValueError("preprocess() is the single-stream entry; use preprocess_batch")
+        if x.shape[0] != self.n_buckets:
+            raise ValueError("x_vqt.len() must equal range.n_buckets()")
+        r = self.preprocess_batch(x[None, None, :], frame_time_ns)
+        n = int(r["peak_count"][0, 0])
+        out = {k: v[0, 0] for k, v in r.items()}
+        out["peaks"] = set(int(i) for i in r["peak_indices"][0, 0, :n])
+        out["peaks_continuous"] = r["peaks_continuous"][0, 0, :n]
+        return out

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "kernel_builder.hpp"
+#include "last_error.hpp"
 #include "pvqt.h"
 #include "vqt_device.cuh"
 
@@ -27,6 +28,12 @@ using namespace pvqt_dev;
 namespace {
 
 thread_local std::string g_last_error;
+
+}  // namespace
+
+void pvqt_detail::set_last_error(const std::string &message) { g_last_error = message; }
+
+namespace {
 
 int fail(pvqt_status st, const std::string &msg)
 {

@@ -1,0 +1,139 @@
+"""GPU parity of the AnalysisState epilogue (K-analysis) against the CPU oracle.
+
+Layer (i) of SURVEY.md section 7: both sides are fed the *same* dB bits (the GPU VQT output), so any
+difference comes from the epilogue itself.  Peak index sets must match exactly in every frame; the
+float state may differ by libm last-ulp effects (device expf/powf/logf vs glibc), bounded below."""
+import numpy as np
+import pytest
+
+import orc
+import pitchvis_b200 as pv
+from pitchvis_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+HOP = synth.HOP_DEFAULT
+FRAME_NS = 16_689_342   # 368 / 22050 s
+
+
+def _oracle_run(db, frame_ns, range_=(55.0, 7, 84), params=None, max_peaks=64):
+    T, NB = db.shape
+    a = orc.OracleAnalysisState(*range_, params=params)
+    out = {"peaks": [], "cont": [], "scene": np.zeros(T, np.float32), "tuning": np.zeros(T, np.float32),
+           "vec": {k: np.zeros((T, NB), np.float32) for k in pv.analysis.VECTOR_FIELDS}}
+    for t in range(T):
+        a.preprocess(db[t], frame_ns)
+        out["peaks"].append(a.peaks)
+        out["cont"].append(a.peaks_continuous)
+        out["scene"][t] = a.smoothed_scene_calmness
+        out["tuning"][t] = a.smoothed_tuning_grid_inaccuracy
+        for k, v in a.vectors().items():
+            out["vec"][k][t] = v
+    return out
+
+
+def _compare(res, s, ref, T):
+    mismatches = []
+    for t in range(T):
+        n = int(res["peak_count"][s, t])
+        got = res["peak_indices"][s, t, :n]
+        if not np.array_equal(got, ref["peaks"][t]):
+            mismatches.append((t, got.tolist(), ref["peaks"][t].tolist()))
+    assert not mismatches, f"{len(mismatches)} frames with different peak sets, first: {mismatches[:3]}"
+    for t in range(T):
+        n = int(res["peak_count"][s, t])
+        np.testing.assert_allclose(res["peaks_continuous"][s, t, :n, 0], ref["cont"][t][:, 0], atol=1e-3)  # bins
+        np.testing.assert_allclose(res["peaks_continuous"][s, t, :n, 1], ref["cont"][t][:, 1], atol=1e-3)  # dB
+    np.testing.assert_allclose(res["smoothed_scene_calmness"][s], ref["scene"], atol=2e-5)
+    np.testing.assert_allclose(res["smoothed_tuning_grid_inaccuracy"][s], ref["tuning"], atol=2e-3)
+    for k in pv.analysis.VECTOR_FIELDS:
+        np.testing.assert_allclose(res[k][s], ref["vec"][k], atol=2e-4, err_msg=k)
+
+
+@pytest.fixture(scope="module")
+def vqt(built_lib):
+    v = pv.Vqt()
+    yield v
+    v.close()
+
+
+def test_zeros_and_wrong_length(built_lib):
+    # analysis.rs:415-428 and the assert at analysis.rs:289
+    a = pv.AnalysisState(pv.VqtRange(55.0, 2, 24))
+    r = a.preprocess(np.zeros(48, np.float32), 1_000_000_000)
+    assert np.all(r["x_vqt_smoothed"] == 0.0) and r["peaks"] == set()
+    with pytest.raises(ValueError):
+        a.preprocess(np.zeros(47, np.float32), 1_000_000_000)
+    a.close()
+
+
+def test_two_close_tones_give_two_peaks(vqt):
+    # lib.rs:16-48 through the GPU VQT and the GPU epilogue (every 6th of the 117 cases)
+    op = orc.default_params()
+    for i in range(int(2.6 * 30), 7 * 30 - 15, 6):
+        f1 = np.float32(55.0) * np.float32(2.0) ** (np.float32(i) / np.float32(30))
+        f2 = np.float32(55.0) * np.float32(2.0) ** np.float32(np.float32(i) / np.float32(30) + np.float32(1 / 12))
+        x_vqt = vqt.calculate_vqt_instant_in_db(orc.test_create_sines(op, [f1, f2]))
+        a = pv.AnalysisState(pv.VqtRange())
+        assert len(a.preprocess(x_vqt, 1100 * 1_000_000)["peaks"]) == 2, i
+        a.close()
+
+
+def test_sequence_matches_oracle(vqt):
+    # BASELINE configs[4] on a 12 s recording (654 frames): same dB bits into both epilogues
+    audio = synth.polyphonic_chords(12.0, 22050.0, seed=0)
+    db = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    T = db.shape[0]
+    a = pv.AnalysisState(pv.VqtRange(), n_streams=1)
+    res = a.preprocess_batch(db, FRAME_NS)
+    ref = _oracle_run(db, FRAME_NS)
+    assert sum(len(p) for p in ref["peaks"]) > 2000
+    _compare(res, 0, ref, T)
+    a.close()
+
+
+def test_batch_split_equals_one_call_and_streams_are_independent(vqt):
+    # state is carried across calls: two calls of T/2 frames == one call of T frames, bit for bit;
+    # and a stream's results do not depend on its neighbours in the batch
+    chords = [synth.polyphonic_chords(4.0, 22050.0, seed=s) for s in (1, 2, 3)]
+    db = vqt.calculate_vqt_streams_in_db(np.stack(chords), HOP)          # [3][T][588]
+    S, T, NB = db.shape
+    one = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    full = one.preprocess_batch(db, FRAME_NS)
+    two = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    h = T // 2
+    first, second = two.preprocess_batch(db[:, :h], FRAME_NS), two.preprocess_batch(db[:, h:], FRAME_NS)
+    for k in full:
+        np.testing.assert_array_equal(full[k], np.concatenate([first[k], second[k]], axis=1), err_msg=k)
+    solo = pv.AnalysisState(pv.VqtRange(), n_streams=1)
+    alone = solo.preprocess_batch(db[1], FRAME_NS)
+    for k in full:
+        np.testing.assert_array_equal(full[k][1], alone[k][0], err_msg=k)
+    ref = _oracle_run(db[2], FRAME_NS)
+    _compare(full, 2, ref, T)
+    for s in (one, two, solo):
+        s.close()
+
+
+def test_smoothing_disabled_and_custom_parameters(vqt):
+    # update_vqt_smoothing_duration(None) -> passthrough (analysis.rs:251-270); non-default thresholds
+    audio = synth.polyphonic_chords(3.0, 22050.0, seed=9)
+    db = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    T = db.shape[0]
+    prm = pv.AnalysisParameters(peak_config=pv.PeakDetectionParameters(6.0, 2.0), highest_bassnote=40,
+                                vqt_smoothing_duration_base=30 * 1_000_000)
+    a = pv.AnalysisState(pv.VqtRange(), prm)
+    a.update_vqt_smoothing_duration(None)
+    res = a.preprocess_batch(db, 33_000_000)
+    np.testing.assert_array_equal(res["x_vqt_smoothed"][0], db)
+    op = orc.analysis_default_params()
+    op.peak_config.min_prominence, op.peak_config.min_height = 6.0, 2.0
+    op.highest_bassnote = 40
+    op.vqt_smoothing_duration_base_ns = 30 * 1_000_000
+    o = orc.OracleAnalysisState(params=op)
+    o.update_vqt_smoothing_duration(None)
+    for t in range(T):
+        o.preprocess(db[t], 33_000_000)
+        n = int(res["peak_count"][0, t])
+        np.testing.assert_array_equal(res["peak_indices"][0, t, :n], o.peaks)
+    a.close()
