@@ -137,3 +137,48 @@ def test_smoothing_disabled_and_custom_parameters(vqt):
         n = int(res["peak_count"][0, t])
         np.testing.assert_array_equal(res["peak_indices"][0, t, :n], o.peaks)
     a.close()
+
+
+def test_config5_full_recording(vqt, oracle_default):
+    """BASELINE configs[4]: the full 60 s recording (3507 frames) through VQT + epilogue.
+
+    Layer (i): identical dB bits into both epilogues -> peak sets must be identical in every frame.
+    Layer (ii): end to end against the all-CPU chain (exact-oracle VQT -> oracle epilogue).  The dB
+    inputs then differ by up to 1e-3 dB, and the thresholds (prominence >= 10, height >= 4) are hard
+    comparisons on EMA-smoothed values, so a near-tie may flip; every flipped peak must be such a
+    near-tie (its oracle prominence or height within 5e-3 dB of the threshold), and there may be at
+    most a handful."""
+    import scipy.signal
+    audio = synth.polyphonic_chords(60.0, 22050.0, seed=0)
+    db = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    T = db.shape[0]
+    assert T == 3507
+    a = pv.AnalysisState(pv.VqtRange())
+    res = a.preprocess_batch(db, FRAME_NS, vectors=False)
+    ref = _oracle_run(db, FRAME_NS)
+    bad = [t for t in range(T)
+           if not np.array_equal(res["peak_indices"][0, t, :int(res["peak_count"][0, t])], ref["peaks"][t])]
+    assert not bad, f"layer (i): {len(bad)} of {T} frames differ, first {bad[:5]}"
+    np.testing.assert_allclose(res["smoothed_scene_calmness"][0], ref["scene"], atol=2e-5)
+    a.close()
+
+    db_cpu = oracle_default.calculate_batch_db(audio, HOP, mode=0)
+    assert np.abs(db_cpu - db).max() <= 1e-3
+    ref2 = _oracle_run(db_cpu, FRAME_NS)
+    flipped = []
+    for t in range(T):
+        got = set(res["peak_indices"][0, t, :int(res["peak_count"][0, t])].tolist())
+        want = set(ref2["peaks"][t].tolist())
+        for p in got ^ want:
+            flipped.append((t, p))
+    assert len(flipped) <= 10, f"layer (ii): {len(flipped)} flipped peaks"
+    for t, p in flipped:
+        sm = ref2["vec"]["x_vqt_smoothed"][t]
+        cfg = (5.0, 3.5) if p <= 28 else (10.0, 4.0)
+        lo, hi = max(p - 2, 1), min(p + 3, 587)
+        cands = [q for q in range(lo, hi) if sm[q - 1] < sm[q] >= sm[q + 1]]
+        margins = []
+        for q in cands:
+            prom = scipy.signal.peak_prominences(sm, [q])[0][0]
+            margins += [abs(prom - cfg[0]), abs(sm[q] - cfg[1])]
+        assert margins and min(margins) < 5e-3, f"frame {t} bin {p}: not a near-tie (margins {margins})"
