@@ -123,6 +123,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank: int, world: int):
     """CPU arm: the oracle's reference-faithful f32 path, all host threads, bounded sample per step."""
     if rank != 0:
@@ -130,7 +138,7 @@ def run_reference(args, rank: int, world: int):
     import orc
     params, audio, hop, n_frames = workload(args.workload, seed=0)
     v = orc.OracleVqt(oracle_params(args.workload))
-    threads = orc.lib().orc_max_threads()
+    threads = host_threads()
     for _ in range(args.warmup):
         v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
     t0 = time.perf_counter()
@@ -154,7 +162,7 @@ def run_reference(args, rank: int, world: int):
 def cpu_baseline(args, audio, hop, n_frames):
     import orc
     v = orc.OracleVqt(oracle_params(args.workload))
-    threads = orc.lib().orc_max_threads()
+    threads = host_threads()
     v.calculate_batch_db(audio, hop, min(n_frames, 256), mode=1, n_threads=threads)  # warm caches / plans
     t0 = time.perf_counter()
     v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
