@@ -190,6 +190,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="chords60", choices=["chords60", "hires60"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
+                    help="L2 flush between timed steps: write a 512 MiB buffer, or write it and read it back "
+                         "(no dirty lines left for the first timed kernel to write back)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -236,7 +239,10 @@ def main():
         pv.calc_db_device(vqt, d_audio, 1, 0, hop, n_frames, d_out)
 
     def flush():
-        chk(lib.pvqt_dev_memset(h, d_flush.ptr, 0, flush_bytes))
+        if args.flush == "write":
+            chk(lib.pvqt_dev_memset(h, d_flush.ptr, 0, flush_bytes))
+        else:
+            chk(lib.pvqt_dev_flush_l2(h, d_flush.ptr, flush_bytes))
 
     for _ in range(args.warmup):
         flush(); step()
@@ -274,8 +280,8 @@ def main():
     chk(lib.pvqt_set_profiling(h, 1))
     for _ in range(args.steps):
         flush(); step()
-    k_ms = (C.c_double * 3)()
-    k_n = (C.c_uint64 * 3)()
+    k_ms = (C.c_double * _ffi.PROFILE_KINDS)()
+    k_n = (C.c_uint64 * _ffi.PROFILE_KINDS)()
     chk(lib.pvqt_get_profile(h, 1, k_ms, k_n))
     chk(lib.pvqt_set_profiling(h, 0))
 
@@ -313,11 +319,20 @@ def main():
         first = int(lib.pvqt_first_sample_used(h))
         union = params.n_fft - first
         bytes_per_frame = 4 * union + 4 * nb                      # 35,120 B at the defaults
-        fft_avg_ms = k_ms[0] / max(1, k_n[0])
-        frames_per_launch = n_frames * args.steps / max(1, k_n[0])
+        # roofline of the dominant kernel (largest share of the step), live CUDA-event durations
+        kinds = [i for i in range(_ffi.PROFILE_KINDS) if k_n[i] > 0]
+        top = max(kinds, key=lambda i: k_ms[i])
+        top_avg_ms = k_ms[top] / k_n[top]
+        frames_per_launch = n_frames * args.steps / k_n[top]
         peak, peak_src = measured_peak_gbs()
-        achieved = bytes_per_frame * frames_per_launch / (fft_avg_ms * 1e-3) / 1e9
+        achieved = bytes_per_frame * frames_per_launch / (top_avg_ms * 1e-3) / 1e9
         whole = bytes_per_frame * n_frames / (statistics.median(step_ms) * 1e-3) / 1e9
+        traffic = None
+        try:  # dram bytes of that kernel from the committed ncu --set full capture, per launch
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get(_ffi.KERNEL_KIND_NAMES[top])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -326,7 +341,9 @@ def main():
                 "workload": f"{args.workload}: 60 s synthetic polyphonic audio per GPU (random chords, seed = rank), "
                             f"default hop {hop}, {n_frames} frames/step/GPU (BASELINE.json configs[1])",
                 "n_fft": params.n_fft, "n_buckets": nb, "hop": hop, "frames_per_step_per_gpu": n_frames,
-                "l2": f"flushed between timed steps ({flush_bytes >> 20} MiB memset)",
+                "l2": f"flushed between timed steps ({flush_bytes >> 20} MiB memset"
+                      + (" followed by a read sweep of the same buffer, so the flush leaves no dirty lines)"
+                         if args.flush != "write" else ")"),
                 "timing": "CUDA events per step on the launching stream, summed; max over ranks",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes),
@@ -335,12 +352,11 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "fft_groups_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bound": "hbm", "kernel": _ffi.KERNEL_KIND_NAMES[top], "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": bytes_per_frame, "frames_per_launch": frames_per_launch,
-                "kernel_avg_ms": fft_avg_ms, "kernel_share_of_step": k_ms[0] / max(1e-9, sum(k_ms)),
-                "other_kernels_avg_ms": {"spmm_kernel": k_ms[1] / max(1, k_n[1]),
-                                         "power_to_db_kernel": k_ms[2] / max(1, k_n[2])},
+                "kernel_avg_ms": top_avg_ms, "kernel_share_of_step": k_ms[top] / max(1e-9, sum(k_ms)),
+                "kernels_avg_ms": {_ffi.KERNEL_KIND_NAMES[i]: k_ms[i] / k_n[i] for i in kinds},
                 "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                 "note": "the path is FP32/shared-memory bound (SURVEY.md 8d); HBM fraction reported as BASELINE asks",
             },

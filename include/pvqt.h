@@ -173,6 +173,10 @@ int pvqt_host_free_pinned(void *p);
 int pvqt_memcpy_h2d(pvqt *v, void *dst, const void *src, size_t bytes, int async);
 int pvqt_memcpy_d2h(pvqt *v, void *dst, const void *src, size_t bytes, int async);
 int pvqt_dev_memset(pvqt *v, void *dst, int value, size_t bytes);
+/* Benchmark hygiene: evict everything from L2 by writing `bytes` (> L2 size) of zeros to `scratch` and
+ * reading them back, so that no dirty lines are left for the next kernel to write back.  Asynchronous on
+ * the handle's stream. */
+int pvqt_dev_flush_l2(pvqt *v, void *scratch, size_t bytes);
 int pvqt_synchronize(pvqt *v);
 int pvqt_event_create(pvqt *v, void **out_event);
 int pvqt_event_destroy(pvqt *v, void *event);
@@ -182,9 +186,20 @@ int pvqt_event_elapsed_ms(pvqt *v, void *start, void *stop, float *ms); /* synch
 uint64_t pvqt_launch_count(const pvqt *v);
 /* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
  * launching stream.  pvqt_get_profile synchronises and returns the summed durations and launch
- * counts since the last reset, indexed 0 = K-fft, 1 = K-spmm, 2 = K-db. */
+ * counts since the last reset, indexed by kernel kind: 0 = K-fft, 1 = K-spmm (unfused fallback),
+ * 2 = K-db (unfused fallback), 3 = K-spmm-db (fused), 4 = K-sdft (sliding partial DFTs),
+ * 5 = K-sdft-combine; both arrays hold PVQT_PROFILE_KINDS entries. */
+#define PVQT_PROFILE_KINDS 8
 int pvqt_set_profiling(pvqt *v, int enabled);
-int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms /*[3]*/, uint64_t *kernel_launches /*[3]*/);
+int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches);
+/* Test / tuning switch: 0 forces the unfused K-spmm + K-db pair, 1 (default) uses K-spmm-db when the
+ * kernel fits one CTA.  Returns the value in effect. */
+int pvqt_set_fused_epilogue(pvqt *v, int enabled);
+/* Test / tuning switch: 0 keeps every window group on the per-frame FFT path, 1 (default) lets groups
+ * whose consumed bins are cheaper as sums of hop-sized partial DFTs shared between overlapping frames take
+ * the K-sdft path in the batched entries (never in the per-frame / independent-frames entries).  Both
+ * paths evaluate the same DFT; they differ by f32 rounding only.  Returns the value in effect. */
+int pvqt_set_sliding_dft(pvqt *v, int enabled);
 
 /* ---- sharding (frame ranges / streams, no collective) ---------- */
 /* Split `n_units` (frames or streams) into `n_parts` contiguous, balanced ranges.  Pure

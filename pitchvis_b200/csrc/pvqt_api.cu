@@ -123,6 +123,9 @@ struct pvqt {
     std::vector<void *> owned;          // device allocations freed on destroy
     FftParams fft{};                    // template (frames/spec filled per launch)
     SpmmParams spmm{};
+    FusedParams fused{};                // K-spmm-db plan (one CTA per tile owns every row)
+    bool fused_capable = false;         // false: the kernel is too large for one CTA -> K-spmm + K-db
+    bool fused_ok = false;              // fused_capable and not switched off (pvqt_set_fused_epilogue)
     int fft_block_threads = 256;
     float ref_db = 0.0f;
     std::vector<uint32_t> col_lo, n_cols, spec_off;
@@ -130,8 +133,17 @@ struct pvqt {
     size_t last_sample_used = 0;        // one past
     uint32_t chunk_frames = 8192;
 
+    // K-sdft plans, one per hop seen (tables depend on the hop); see select_sdft()
+    struct SdftPlan {
+        size_t hop = 0;
+        std::vector<int> group_index;      // window groups this hop has tables for
+        std::vector<SdftGroup> groups;     // device tables
+    };
+    std::vector<SdftPlan> sdft_plans;
+    bool sdft_enabled = true;              // pvqt_set_sliding_dft
+
     // scratch
-    DeviceBuffer spec, power, d_audio, d_out;
+    DeviceBuffer spec, power, d_audio, d_out, sdft_c, sdft_r;
     std::atomic<uint64_t> launches{0};
 
     // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
@@ -161,6 +173,8 @@ cudaError_t upload(pvqt *v, const std::vector<T> &host, const T **dev)
     *dev = static_cast<const T *>(p);
     return cudaSuccess;
 }
+
+int build_fused_plan(pvqt *v);
 
 int build_device_plan(pvqt *v)
 {
@@ -342,7 +356,220 @@ int build_device_plan(pvqt *v)
 
     if ((e = configure_kernels(max_cols)) != cudaSuccess)
         return cuda_fail(e, "configure kernels (is this an sm_100a device?)");
+    return build_fused_plan(v);
+}
+
+// ---- K-spmm-db plan: row pairs sorted by band length, dealt to warps, bank-conflict-free lanes ----
+int build_fused_plan(pvqt *v)
+{
+    const auto &groups = v->kernel.window_groups;
+    const FftParams &F = v->fft;
+    struct Unit {
+        int col0 = 0, len = 0, ncol0 = 0, nlen = 0;   // bands in spectrum columns
+        int first_row = 0, n_rows = 0;                // output rows
+        int group = 0, local_row = 0;
+    };
+    std::vector<Unit> units;
+    int first_row = 0, n_cols = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const auto &g = groups[gi];
+        const int spec = F.group[gi].spec_offset, lo = F.group[gi].col_lo;
+        n_cols = std::max(n_cols, spec + F.group[gi].col_hi - lo + 1);
+        for (int r0 = 0; r0 < g.filter_bank.rows; r0 += kRowsPerLane) {
+            Unit u;
+            u.group = (int)gi; u.local_row = r0; u.first_row = first_row + r0;
+            u.n_rows = std::min(kRowsPerLane, g.filter_bank.rows - r0);
+            int a0 = 1 << 30, a1 = -1, n0 = 1 << 30, n1 = -1;
+            for (int q = 0; q < u.n_rows; ++q) {
+                const int r = r0 + q;
+                const int s = g.filter_bank.indptr[r], e = g.filter_bank.indptr[r + 1];
+                if (e > s) {
+                    a0 = std::min(a0, spec + g.filter_bank.indices[s] - lo);
+                    a1 = std::max(a1, spec + g.filter_bank.indices[e - 1] - lo + 1);
+                }
+                if (g.negative_filter_bank.nnz() > 0) {
+                    const int ns = g.negative_filter_bank.indptr[r], ne = g.negative_filter_bank.indptr[r + 1];
+                    if (ne > ns) {
+                        n0 = std::min(n0, spec + g.negative_filter_bank.indices[ns] - lo);
+                        n1 = std::max(n1, spec + g.negative_filter_bank.indices[ne - 1] - lo + 1);
+                    }
+                }
+            }
+            if (a1 >= 0) { u.col0 = a0; u.len = a1 - a0; }
+            if (n1 >= 0) { u.ncol0 = n0; u.nlen = n1 - n0; }
+            units.push_back(u);
+        }
+        first_row += g.filter_bank.rows;
+    }
+    std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.len + a.nlen > b.len + b.nlen; });
+    const int n_warps = (int)((units.size() + 31) / 32);
+    n_cols = std::min<int>((n_cols + 7) & ~7, F.spec_stride);
+    v->fused_capable = v->fused_ok = fused_supported(n_warps, n_cols, (int)v->kernel.n_buckets);
+    if (!v->fused_ok) return PVQT_OK;
+
+    std::vector<FusedWarp> warps((size_t)n_warps);
+    std::vector<int4> lane_meta((size_t)n_warps * 32, make_int4(0, 0, 0, 0));
+    std::vector<int2> lane_rows((size_t)n_warps * 32, make_int2(0, 0));
+    std::vector<float4> values;
+    for (int w = 0; w < n_warps; ++w) {
+        // A lane reads the 64-byte record of column col0 + j at slot j; its bank group depends on the column
+        // modulo 8 only, and all lanes advance together, so a quarter-warp (one LDS.128 wavefront) is
+        // conflict-free for the whole band iff its lanes start on distinct residues (or the same column).
+        // Units are placed greedily; a unit may start up to 7 columns early (zero coefficients) to get a
+        // free residue.
+        const int u0 = w * 32, u1 = std::min<int>((int)units.size(), u0 + 32);
+        int residue_col[4][8];
+        int count[4] = {0, 0, 0, 0};
+        for (auto &q : residue_col) for (int &c : q) c = -1;
+        int lane_of[32];
+        for (int i = u0; i < u1; ++i) {
+            Unit &u = units[i];
+            int best_q = -1, best_shift = 0;
+            for (int shift = 0; shift < 8 && best_q < 0 && u.len > 0; ++shift) {
+                const int c = u.col0 - shift;
+                if (c < 0) break;
+                for (int q = 0; q < 4; ++q) {
+                    if (count[q] >= 8) continue;
+                    const int held = residue_col[q][c & 7];
+                    if (held != -1 && held != c) continue;
+                    if (best_q < 0 || count[q] < count[best_q]) { best_q = q; best_shift = shift; }
+                }
+            }
+            if (best_q < 0) {  // empty unit, or no conflict-free slot: any free lane
+                for (int q = 0; q < 4; ++q)
+                    if (count[q] < 8 && (best_q < 0 || count[q] < count[best_q])) best_q = q;
+                best_shift = 0;
+            }
+            if (u.len > 0) {
+                u.col0 -= best_shift;
+                u.len += best_shift;
+                if (residue_col[best_q][u.col0 & 7] == -1) residue_col[best_q][u.col0 & 7] = u.col0;
+            }
+            lane_of[i - u0] = best_q * 8 + count[best_q]++;
+        }
+        int width = 0, nwidth = 0;
+        for (int i = u0; i < u1; ++i) { width = std::max(width, units[i].len); nwidth = std::max(nwidth, units[i].nlen); }
+        width = (width + 1) & ~1;  // the kernel walks two slots per trip
+        FusedWarp &W = warps[(size_t)w];
+        W.width = width;
+        W.nwidth = nwidth;
+        W.val_base = (int)(values.size() / 32);
+        values.resize(values.size() + (size_t)width * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+        W.nval_base = (int)(values.size() / 32);
+        values.resize(values.size() + (size_t)nwidth * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int i = u0; i < u1; ++i) {
+            const Unit &u = units[i];
+            const int l = lane_of[i - u0];
+            const auto &g = groups[(size_t)u.group];
+            const int spec = F.group[u.group].spec_offset, lo = F.group[u.group].col_lo;
+            lane_meta[(size_t)w * 32 + l] = make_int4(u.col0, u.len, u.ncol0, u.nlen);
+            lane_rows[(size_t)w * 32 + l] = make_int2(u.first_row, u.n_rows);
+            for (int q = 0; q < u.n_rows; ++q) {
+                const int r = u.local_row + q;
+                for (int e = g.filter_bank.indptr[r]; e < g.filter_bank.indptr[r + 1]; ++e) {
+                    const int j = spec + g.filter_bank.indices[e] - lo - u.col0;
+                    float4 &slot = values[((size_t)W.val_base + j) * 32 + l];
+                    (q == 0 ? slot.x : slot.z) = g.filter_bank.data[e].real();
+                    (q == 0 ? slot.y : slot.w) = g.filter_bank.data[e].imag();
+                }
+                if (u.nlen > 0)
+                    for (int e = g.negative_filter_bank.indptr[r]; e < g.negative_filter_bank.indptr[r + 1]; ++e) {
+                        const int j = spec + g.negative_filter_bank.indices[e] - lo - u.ncol0;
+                        float4 &slot = values[((size_t)W.nval_base + j) * 32 + l];
+                        // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg)
+                        (q == 0 ? slot.x : slot.z) = g.negative_filter_bank.data[e].real();
+                        (q == 0 ? slot.y : slot.w) = -g.negative_filter_bank.data[e].imag();
+                    }
+            }
+        }
+    }
+    values.resize(values.size() + (size_t)2 * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
+
+    FusedParams &P = v->fused;
+    std::memset(&P, 0, sizeof(P));
+    cudaError_t e;
+    if ((e = upload(v, warps, &P.warps)) != cudaSuccess) return cuda_fail(e, "upload fused warps");
+    if ((e = upload(v, lane_meta, &P.lane_meta)) != cudaSuccess) return cuda_fail(e, "upload fused lane_meta");
+    if ((e = upload(v, lane_rows, &P.lane_rows)) != cudaSuccess) return cuda_fail(e, "upload fused lane_rows");
+    if ((e = upload(v, values, &P.values)) != cudaSuccess) return cuda_fail(e, "upload fused values");
+    P.n_warps = n_warps;
+    P.n_buckets = (int32_t)v->kernel.n_buckets;
+    P.spec_stride = F.spec_stride;
+    P.n_cols = n_cols;
+    P.ref_db = v->ref_db;
+    if ((e = configure_fused(n_warps, n_cols, P.n_buckets)) != cudaSuccess)
+        return cuda_fail(e, "configure spmm_db_fused_kernel");
     return PVQT_OK;
+}
+
+// ---- K-sdft: which window groups take the sliding partial-DFT path for this (hop, frames per stream) ----
+// Per frame the FFT path costs about 2 N log2 N pipe operations and touches shared memory three times per
+// point; the sliding path costs 2 * nk * hop FMAs (one chunk per new frame) plus the combine, and reads
+// each sample once.  It pays when the kernel consumes few bins of a long window and frames overlap a lot
+// (group 0 at the defaults: 61 bins of an 8192-point FFT, hop 368).
+bool sdft_worthwhile(size_t n_window, size_t nk, size_t hop, size_t frames_per_stream)
+{
+    if (hop < 16 || hop * 4 > n_window || nk == 0 || nk > 1024) return false;
+    const double q = (double)(n_window / hop);
+    const double sdft = 2.4 * (double)nk * (double)hop * ((double)frames_per_stream + q) + 8.0 * nk * (q + 1) * frames_per_stream;
+    const double fft = 1.6 * (double)n_window * std::log2((double)n_window) * (double)frames_per_stream;
+    return sdft < 0.7 * fft;
+}
+
+const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
+{
+    *status = PVQT_OK;
+    for (const auto &p : v->sdft_plans)
+        if (p.hop == hop) return &p;
+    if (v->sdft_plans.size() >= 8) return nullptr;  // tables are never evicted: bound them
+    pvqt::SdftPlan plan;
+    plan.hop = hop;
+    const auto &groups = v->kernel.window_groups;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const size_t n = groups[gi].window_size();
+        const size_t nk = v->n_cols[gi];
+        if (!sdft_worthwhile(n, nk, hop, 1u << 20)) continue;  // not even for a long stream
+        SdftGroup g{};
+        g.window_begin = (int32_t)groups[gi].window_begin;
+        g.n_window = (int32_t)n;
+        g.k_lo = (int32_t)v->col_lo[gi];
+        g.nk = (int32_t)nk;
+        g.spec_offset = (int32_t)v->spec_off[gi];
+        g.hop = (int32_t)hop;
+        g.q = (int32_t)(n / hop);
+        g.rem = (int32_t)(n % hop);
+        g.n_blocks = (int32_t)((hop + 15) / 16);
+        g.hop_pad = g.n_blocks * 16;
+        if (sdft_smem_bytes(g.hop_pad) > 200 * 1024 || sdft_combine_smem_bytes(g.q, g.nk) > 200 * 1024) continue;
+        auto tw = [&](uint64_t k, uint64_t m) {  // exp(-2 pi i k m / N), argument reduced exactly
+            const uint64_t r = (k * m) % n;
+            const double a = -2.0 * kPi * (double)r / (double)n;
+            return make_float2((float)std::cos(a), (float)std::sin(a));
+        };
+        std::vector<float2> ta((size_t)g.n_blocks * nk), tb((size_t)16 * nk);
+        std::vector<double2> ph((size_t)(g.q + 1) * nk);
+        for (size_t k = 0; k < nk; ++k) {
+            const uint64_t ka = g.k_lo + k;
+            for (int a = 0; a < g.n_blocks; ++a) ta[(size_t)a * nk + k] = tw(ka, 16ull * a);
+            for (int b = 0; b < 16; ++b) tb[(size_t)b * nk + k] = tw(ka, b);
+            for (int i = 0; i <= g.q; ++i) {
+                const uint64_t r = (ka * (uint64_t)i * hop) % n;
+                const double a = -2.0 * kPi * (double)r / (double)n;
+                ph[(size_t)i * nk + k] = make_double2(std::cos(a), std::sin(a));
+            }
+        }
+        cudaError_t e;
+        if ((e = upload(v, ta, &g.tw_a)) != cudaSuccess || (e = upload(v, tb, &g.tw_b)) != cudaSuccess ||
+            (e = upload(v, ph, &g.phase)) != cudaSuccess || (e = configure_sdft(g.hop_pad)) != cudaSuccess ||
+            (e = configure_sdft_combine(g.q, g.nk)) != cudaSuccess) {
+            *status = cuda_fail(e, "build K-sdft plan");
+            return nullptr;
+        }
+        plan.group_index.push_back((int)gi);
+        plan.groups.push_back(g);
+    }
+    v->sdft_plans.push_back(std::move(plan));
+    return &v->sdft_plans.back();
 }
 
 void prof_begin(pvqt *v, int kind, cudaStream_t stream)
@@ -381,65 +608,164 @@ int reserve_scratch(pvqt *v, size_t frames, bool need_power, cudaStream_t stream
     return PVQT_OK;
 }
 
-// Launch K-fft, K-spmm and K-db for the frames `(n_streams, frames_per_stream, hop)` describe.
+// Launch the kernels for the frames `(n_streams, frames_per_stream, hop)` describe:
+//   [K-sdft partial] -> K-fft (remaining groups) -> [K-sdft combine] -> K-spmm-db   (or K-spmm + K-db)
+// every arrow a programmatic dependent launch.  Work is cut into launches of at most chunk_frames frames:
+// whole streams when a stream is shorter than that, else frame ranges of one stream.
 int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
                size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream)
 {
     const size_t total = n_streams * frames_per_stream;
     if (total == 0) return PVQT_OK;
-    if (frames_per_stream > 0xffffffffull) return fail(PVQT_INVALID_ARGUMENT, "frames_per_stream too large");
+    if (frames_per_stream > 0xffffffffull || n_streams > 0xffffffffull)
+        return fail(PVQT_INVALID_ARGUMENT, "too many frames per stream or streams");
     const size_t nb = v->kernel.n_buckets;
-    const uint32_t chunk = v->chunk_frames;  // multiple of kTileFrames
-    const size_t chunk_now = std::min<size_t>(total, chunk);
+    const size_t chunk = v->chunk_frames;  // multiple of kTileFrames
     const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
     if (!d_spec_out) {
-        int rc = reserve_scratch(v, chunk_now, d_power == nullptr, stream);
+        int rc = reserve_scratch(v, std::min(total, chunk), d_power == nullptr && !v->fused_ok, stream);
         if (rc) return rc;
     }
-    for (size_t f0 = 0; f0 < total; f0 += chunk) {
-        const uint32_t n = (uint32_t)std::min<size_t>(chunk, total - f0);
-        FftParams fp = v->fft;
-        fp.frames.audio = d_audio;
-        fp.frames.stream_stride = stream_stride;
-        fp.frames.hop = hop;
-        fp.frames.frames_per_stream = (uint32_t)frames_per_stream;
-        fp.frames.n_frames = n;
-        fp.frames.first_frame = f0;
-        fp.spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(v->spec.ptr);
-        int ctas = 0;
-        for (int g = 0; g < fp.n_groups; ++g) {
-            fp.group[g].cta_begin = ctas;
-            ctas += (int)((n + fp.group[g].frames_per_cta - 1) / fp.group[g].frames_per_cta);
+
+    // window groups on the sliding partial-DFT path for this call
+    const pvqt::SdftPlan *plan = nullptr;
+    std::vector<int> sdft_groups;  // indices into plan->groups
+    if (v->sdft_enabled && frames_per_stream > 1) {
+        int st = PVQT_OK;
+        plan = sdft_plan_for(v, hop, &st);
+        if (st != PVQT_OK) return st;
+        if (plan)
+            for (size_t i = 0; i < plan->groups.size(); ++i)
+                if (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream))
+                    sdft_groups.push_back((int)i);
+    }
+    auto on_sdft = [&](int gi) {
+        for (int i : sdft_groups)
+            if (plan->group_index[(size_t)i] == gi) return true;
+        return false;
+    };
+
+    const bool by_stream = frames_per_stream <= chunk;
+    const size_t streams_per_launch = by_stream ? std::max<size_t>(1, chunk / frames_per_stream) : 1;
+    for (size_t s0 = 0; s0 < n_streams; s0 += streams_per_launch) {
+        const size_t ns = std::min(streams_per_launch, n_streams - s0);
+        for (size_t t0 = 0; t0 < frames_per_stream; t0 += chunk) {
+            const size_t nf = std::min(chunk, frames_per_stream - t0);  // == frames_per_stream when by_stream
+            const size_t f0 = s0 * frames_per_stream + t0;               // flat index of the launch's first frame
+            const uint32_t n = (uint32_t)(ns * nf);
+            float *spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(v->spec.ptr);
+
+            // ---- K-sdft partial sums ----
+            std::vector<SdftParams> sd;
+            for (int i : sdft_groups) {
+                SdftParams sp{};
+                sp.g = plan->groups[(size_t)i];
+                sp.audio = d_audio;
+                sp.stream_stride = stream_stride;
+                sp.valid_samples = (frames_per_stream - 1) * hop + (size_t)v->params.n_fft;
+                sp.first_stream = (uint32_t)s0;
+                sp.n_streams = (uint32_t)ns;
+                sp.first_frame = (uint32_t)t0;
+                sp.frames = (uint32_t)nf;
+                sp.rows_per_stream = (uint32_t)(nf + sp.g.q);
+                sp.spec_stride = v->fft.spec_stride;
+                sp.spec = spec;
+                sd.push_back(sp);
+            }
+            if (!sd.empty()) {
+                size_t need = 0;
+                for (const auto &sp : sd) need += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(double2);
+                if (v->sdft_c.reserve(need) != cudaSuccess || v->sdft_r.reserve(need) != cudaSuccess)
+                    return cuda_fail(cudaGetLastError(), "allocate K-sdft scratch");
+                size_t off = 0;
+                for (auto &sp : sd) {
+                    sp.partial_c = reinterpret_cast<double2 *>(static_cast<char *>(v->sdft_c.ptr) + off);
+                    sp.partial_r = reinterpret_cast<double2 *>(static_cast<char *>(v->sdft_r.ptr) + off);
+                    off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(double2);
+                    prof_begin(v, 4, stream);
+                    cudaError_t e = launch_sdft_partial(sp, stream);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
+                    prof_end(v, stream);
+                    v->launches.fetch_add(1);
+                }
+            }
+
+            // ---- K-fft for the other groups ----
+            FftParams fp = v->fft;
+            fp.frames.audio = d_audio;
+            fp.frames.stream_stride = stream_stride;
+            fp.frames.hop = hop;
+            fp.frames.frames_per_stream = (uint32_t)frames_per_stream;
+            fp.frames.n_frames = n;
+            fp.frames.first_frame = f0;
+            fp.spec = spec;
+            fp.wait_prior = sd.empty() ? 0 : 1;
+            int ctas = 0, kept = 0;
+            for (int g = 0; g < v->fft.n_groups; ++g) {
+                if (on_sdft(g)) continue;
+                fp.group[kept] = v->fft.group[g];
+                fp.group[kept].cta_begin = ctas;
+                ctas += (int)((n + fp.group[kept].frames_per_cta - 1) / fp.group[kept].frames_per_cta);
+                ++kept;
+            }
+            fp.n_groups = kept;
+            if (kept > 0) {
+                prof_begin(v, 0, stream);
+                cudaError_t e = launch_fft(fp, ctas, v->fft_block_threads, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch fft_groups_kernel");
+                prof_end(v, stream);
+                v->launches.fetch_add(1);
+            }
+
+            // ---- K-sdft combine: the sliding groups' bins join the FFT groups' in the spectrum tiles ----
+            for (const auto &sp : sd) {
+                prof_begin(v, 5, stream);
+                cudaError_t e = launch_sdft_combine(sp, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch sdft_combine_kernel");
+                prof_end(v, stream);
+                v->launches.fetch_add(1);
+            }
+            if (d_spec_out) continue;
+
+            cudaError_t e;
+            if (v->fused_ok) {
+                FusedParams up = v->fused;
+                up.n_frames = n;
+                up.n_tiles = (n + kTileFrames - 1) / kTileFrames;
+                up.spec = spec;
+                up.out_db = d_out + f0 * nb;
+                up.power = d_power ? d_power + f0 * nb : nullptr;
+                prof_begin(v, 3, stream);
+                e = launch_spmm_db_fused(up, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_fused_kernel");
+                prof_end(v, stream);
+                v->launches.fetch_add(1);
+                continue;
+            }
+
+            SpmmParams sp = v->spmm;
+            sp.n_frames = n;
+            sp.n_tiles = (n + kTileFrames - 1) / kTileFrames;
+            sp.spec = spec;
+            sp.power = d_power ? d_power + f0 * nb : static_cast<float *>(v->power.ptr);
+            prof_begin(v, 1, stream);
+            e = launch_spmm(sp, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "launch spmm_kernel");
+            prof_end(v, stream);
+            v->launches.fetch_add(1);
+
+            DbParams dp{};
+            dp.power = sp.power;
+            dp.out_db = d_out + f0 * nb;
+            dp.n_frames = n;
+            dp.n_buckets = (int32_t)nb;
+            dp.ref_db = v->ref_db;
+            prof_begin(v, 2, stream);
+            e = launch_power_to_db(dp, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "launch power_to_db_kernel");
+            prof_end(v, stream);
+            v->launches.fetch_add(1);
         }
-        prof_begin(v, 0, stream);
-        cudaError_t e = launch_fft(fp, ctas, v->fft_block_threads, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch fft_groups_kernel");
-        prof_end(v, stream);
-        v->launches.fetch_add(1);
-        if (d_spec_out) continue;
-
-        SpmmParams sp = v->spmm;
-        sp.n_frames = n;
-        sp.n_tiles = (n + kTileFrames - 1) / kTileFrames;
-        sp.spec = fp.spec;
-        sp.power = d_power ? d_power + f0 * nb : static_cast<float *>(v->power.ptr);
-        prof_begin(v, 1, stream);
-        e = launch_spmm(sp, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch spmm_kernel");
-        prof_end(v, stream);
-        v->launches.fetch_add(1);
-
-        DbParams dp{};
-        dp.power = sp.power;
-        dp.out_db = d_out + f0 * nb;
-        dp.n_frames = n;
-        dp.n_buckets = (int32_t)nb;
-        dp.ref_db = v->ref_db;
-        prof_begin(v, 2, stream);
-        e = launch_power_to_db(dp, stream);
-        if (e != cudaSuccess) return cuda_fail(e, "launch power_to_db_kernel");
-        prof_end(v, stream);
-        v->launches.fetch_add(1);
     }
     return PVQT_OK;
 }
@@ -590,7 +916,7 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         const size_t frames = n_streams * frames_per_stream;
         PVQT_CUDA(v->d_audio.reserve(audio_samples * sizeof(float)));
         PVQT_CUDA(v->d_out.reserve(frames * J.nb * sizeof(float)));
-        int rc = reserve_scratch(v, frames, true, v->stream);
+        int rc = reserve_scratch(v, frames, !v->fused_ok, v->stream);
         if (rc) return rc;
         auto enqueue = [&]() -> int {
             int r = fork_streams(v, ev);
@@ -604,7 +930,7 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         key.audio = audio; key.out = out; key.n_streams = n_streams; key.stream_stride = stream_stride;
         key.n_samples = n_samples; key.hop = hop; key.frames_per_stream = frames_per_stream;
         key.generations = v->d_audio.generation * 1000003u + v->d_out.generation * 10007u + v->spec.generation * 101u +
-                          v->power.generation;
+                          v->power.generation + v->sdft_c.generation * 7u + v->sdft_r.generation * 13u;
         if (v->use_graphs && !v->profiling) {
             if (!(v->graph_exec && key == v->graph_key)) {
                 if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
@@ -849,6 +1175,8 @@ void pvqt_destroy(pvqt *v)
     for (void *p : v->owned) cudaFree(p);
     v->spec.release();
     v->power.release();
+    v->sdft_c.release();
+    v->sdft_r.release();
     v->d_audio.release();
     v->d_out.release();
     delete v;
@@ -990,6 +1318,15 @@ int pvqt_dev_memset(pvqt *v, void *dst, int value, size_t bytes)
     PVQT_CUDA(cudaMemsetAsync(dst, value, bytes, v->stream));
     return PVQT_OK;
 }
+int pvqt_dev_flush_l2(pvqt *v, void *scratch, size_t bytes)
+{
+    if (!v || !scratch || bytes < 16) return fail(PVQT_INVALID_ARGUMENT, "null handle or scratch");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    PVQT_CUDA(cudaMemsetAsync(scratch, 0, bytes, v->stream));
+    PVQT_CUDA(launch_read_sweep(scratch, bytes, static_cast<unsigned *>(scratch), v->stream));
+    return PVQT_OK;
+}
+
 int pvqt_synchronize(pvqt *v)
 {
     if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
@@ -1037,12 +1374,28 @@ int pvqt_set_profiling(pvqt *v, int enabled)
     return PVQT_OK;
 }
 
-int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms /*[3]*/, uint64_t *kernel_launches /*[3]*/)
+int pvqt_set_fused_epilogue(pvqt *v, int enabled)
+{
+    if (!v) return 0;
+    v->fused_ok = v->fused_capable && enabled != 0;
+    if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
+    return v->fused_ok ? 1 : 0;
+}
+
+int pvqt_set_sliding_dft(pvqt *v, int enabled)
+{
+    if (!v) return 0;
+    v->sdft_enabled = enabled != 0;
+    if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
+    return v->sdft_enabled ? 1 : 0;
+}
+
+int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches)
 {
     if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
     PVQT_CUDA(cudaSetDevice(v->device));
-    double ms[3] = {0.0, 0.0, 0.0};
-    uint64_t n[3] = {0, 0, 0};
+    double ms[PVQT_PROFILE_KINDS] = {};
+    uint64_t n[PVQT_PROFILE_KINDS] = {};
     for (const auto &t : v->timed) {
         float e = 0.f;
         PVQT_CUDA(cudaEventSynchronize(t.b));
@@ -1054,7 +1407,7 @@ int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms /*[3]*/, uint64_t *ke
         for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
         v->timed.clear();
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < PVQT_PROFILE_KINDS; ++i) {
         if (kernel_ms) kernel_ms[i] = ms[i];
         if (kernel_launches) kernel_launches[i] = n[i];
     }

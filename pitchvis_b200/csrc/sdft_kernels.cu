@@ -1,0 +1,297 @@
+// sdft_kernels.cu -- K-sdft: the consumed FFT bins of a window group as sums of hop-sized partial DFTs
+// shared by overlapping frames (see SdftGroup in vqt_device.cuh for the algebra).
+//
+//   sdft_partial_kernel   C[row][k], R[row][k] for every chunk row the launch's frames touch; one lane per
+//                         bin, the chunk samples broadcast from shared memory, FFMA2 on (re, im) pairs
+//   sdft_combine_kernel   X_t[k] = sum_i phase[i][k] C[t+i][k] (+ remainder), written into the tiled
+//                         spectrum layout K-spmm-db stages -- the same place K-fft writes its bins
+//
+// Replaces, for the groups it is selected for, the realfft call of vqt.rs:884-887: same unnormalised
+// forward DFT, X[k] = sum_n x[n] exp(-2 pi i k n / N), summed chunk by chunk in f32.
+#include "device_helpers.cuh"
+#include "vqt_device.cuh"
+
+namespace pvqt_dev {
+namespace {
+
+// 4-byte cp.async with zero fill: src_bytes = 0 writes zeros without reading.
+__device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gmem_src, unsigned src_bytes)
+{
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+
+// Partial sums.  Lane = bin, kSdftRowsPerWarp chunk rows per warp.  The CTA's chunk rows are staged with
+// cp.async (every copy in flight at once: one DRAM round trip for the whole stage).  Inside a 16-sample
+// block the packed FFMA2 lanes hold the even / odd samples' contributions -- both operands are natural
+// register pairs: two consecutive samples of one LDS.128 and the matching pair of B twiddles -- added at
+// the end of the block, times A[a], into the chunk's running sum.  All f32; the long sum over chunks is
+// done in f64 by the combine step, which is where the accuracy of the path is decided.
+__global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __grid_constant__ SdftParams P)
+{
+    extern __shared__ __align__(16) float4 sdft_smem[];
+    __shared__ const float *row_src[kSdftRowsPerCta];   // first sample of the row (nullptr: row past the end)
+    __shared__ uint32_t row_valid[kSdftRowsPerCta];     // samples of the row inside the stream
+    float *xs = reinterpret_cast<float *>(sdft_smem);  // [kSdftRowsPerCta][hop_pad]
+    const SdftGroup &G = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = blockIdx.y * 64 + (warp & 1) * 32 + lane;   // bin index inside the group's consumed range
+    const int rg = warp >> 1;                                   // row group of this warp
+    const bool active = k < G.nk;
+    const uint32_t total_rows = P.n_streams * P.rows_per_stream;
+    const uint32_t row0 = blockIdx.x * kSdftRowsPerCta;
+
+    pdl_launch_dependents();  // K-fft of the other groups may run beside this kernel
+
+    // row r = (stream, chunk c) covers samples [c H + window_begin, + H) of its stream
+    if (tid < kSdftRowsPerCta) {
+        const uint32_t row = row0 + tid;
+        const float *src = nullptr;
+        uint32_t valid = 0;
+        if (row < total_rows) {
+            const uint32_t s = row / P.rows_per_stream;
+            const uint32_t c = P.first_frame + (row - s * P.rows_per_stream);
+            const uint64_t base = (uint64_t)c * G.hop + G.window_begin;
+            src = P.audio + (uint64_t)(P.first_stream + s) * P.stream_stride + base;
+            valid = base < P.valid_samples ? (uint32_t)min((uint64_t)G.hop, P.valid_samples - base) : 0u;
+        }
+        row_src[tid] = src;
+        row_valid[tid] = valid;
+    }
+    __syncthreads();
+    for (int r = 0; r < kSdftRowsPerCta; ++r) {
+        const float *src = row_src[r];
+        const uint32_t valid = row_valid[r];
+        float *dst = xs + r * G.hop_pad;
+        for (int j = tid; j < G.hop_pad; j += kSdftThreads) {
+            const bool ok = (uint32_t)j < valid;
+            cp_async4_zfill(dst + j, ok ? src + j : P.audio, ok ? 4u : 0u);
+        }
+    }
+
+    // B twiddles as (even sample, odd sample) pairs: bre[m] = (Re B[2m], Re B[2m+1]), bim likewise
+    float2 bre[8], bim[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const float2 b0 = active ? __ldg(G.tw_b + (2 * m) * G.nk + k) : make_float2(0.f, 0.f);
+        const float2 b1 = active ? __ldg(G.tw_b + (2 * m + 1) * G.nk + k) : make_float2(0.f, 0.f);
+        bre[m] = make_float2(b0.x, b1.x);
+        bim[m] = make_float2(b0.y, b1.y);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    float2 acc[kSdftRowsPerWarp];
+#pragma unroll
+    for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) acc[ch] = make_float2(0.f, 0.f);
+    const int ra = G.rem >> 4, rb = G.rem & 15;
+    const int row_stride4 = G.hop_pad >> 2;
+    const float4 *x4 = sdft_smem + (size_t)(rg * kSdftRowsPerWarp) * row_stride4;
+    const float *x1 = xs + (size_t)(rg * kSdftRowsPerWarp) * G.hop_pad;
+    const uint32_t my_row0 = row0 + rg * kSdftRowsPerWarp;
+    float2 A = active ? __ldg(G.tw_a + k) : make_float2(0.f, 0.f);
+
+    for (int a = 0; a < G.n_blocks; ++a) {
+        const float2 An = (active && a + 1 < G.n_blocks) ? __ldg(G.tw_a + (a + 1) * G.nk + k) : make_float2(0.f, 0.f);
+        if (a == ra) {
+            // the remainder ends in this block: R = running sum + A * (first rb samples of the block)
+#pragma unroll
+            for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) {
+                float2 sp = make_float2(0.f, 0.f);
+                for (int b = 0; b < rb; ++b) {
+                    const float x = x1[ch * G.hop_pad + a * 16 + b];
+                    const float2 w = __ldg(G.tw_b + b * G.nk + (active ? k : 0));
+                    sp = __ffma2_rn(w, make_float2(x, x), sp);
+                }
+                const float2 r = cadd(acc[ch], cmul(sp, A));
+                const uint32_t row = my_row0 + ch;
+                if (active && row < total_rows) P.partial_r[(size_t)row * G.nk + k] = make_double2((double)r.x, (double)r.y);
+            }
+        }
+        float2 sre[kSdftRowsPerWarp], sim[kSdftRowsPerWarp];
+#pragma unroll
+        for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) sre[ch] = sim[ch] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) {
+                const float4 x = x4[ch * row_stride4 + g];  // the same address in every lane: broadcast
+                const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
+                sre[ch] = __ffma2_rn(bre[2 * g], x01, sre[ch]);
+                sim[ch] = __ffma2_rn(bim[2 * g], x01, sim[ch]);
+                sre[ch] = __ffma2_rn(bre[2 * g + 1], x23, sre[ch]);
+                sim[ch] = __ffma2_rn(bim[2 * g + 1], x23, sim[ch]);
+            }
+        }
+        x4 += 4;
+#pragma unroll
+        for (int ch = 0; ch < kSdftRowsPerWarp; ++ch)
+            acc[ch] = cadd(acc[ch], cmul(make_float2(sre[ch].x + sre[ch].y, sim[ch].x + sim[ch].y), A));
+        A = An;
+    }
+
+    if (active) {
+#pragma unroll
+        for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) {
+            const uint32_t row = my_row0 + ch;
+            if (row < total_rows)
+                P.partial_c[(size_t)row * G.nk + k] = make_double2((double)acc[ch].x, (double)acc[ch].y);
+        }
+    }
+}
+
+// One CTA per 8-frame tile: the q + 8 chunk rows the tile's frames need are staged once (cp.async), then
+// thread (frame, bin) sums its q (+1) rows in f64 (the rounding of this long sum is what limits the
+// accuracy of the path: in f32 it costs 4x the error).
+__global__ void __launch_bounds__(kTileFrames * 64) sdft_combine_kernel(const __grid_constant__ SdftParams P)
+{
+    extern __shared__ __align__(16) double2 comb_smem[];   // [q + 7 rows][nk] C, [8][nk] R, [q + 1][nk] phase
+    const SdftGroup &G = P.g;
+    pdl_launch_dependents();
+    const uint32_t n_frames = P.n_streams * P.frames;
+    const uint32_t lf0 = blockIdx.x * kTileFrames;
+    const int fi = threadIdx.x >> 6;
+    const uint32_t lf = lf0 + fi;
+    const int n_c = G.q + kTileFrames - 1;  // C rows per frame-aligned run; R rows: one per frame
+    double2 *cs = comb_smem, *rs = comb_smem + (size_t)n_c * G.nk, *ph = rs + (size_t)kTileFrames * G.nk;
+    for (int i = threadIdx.x; i < (G.q + 1) * G.nk; i += blockDim.x) cp_async16(ph + i, G.phase + i);  // plan data
+    // Frames of a tile may straddle two streams: stage per frame-row with the row index computed per frame.
+    // Row of (frame f, i): stream(f) * rows_per_stream + t(f) + i.  For frames of one stream the rows of
+    // consecutive frames overlap; stage the run [row(first frame), + q + 7) and let other streams' frames
+    // (rare: only at stream boundaries) read global memory directly.
+    const uint32_t s0 = lf0 / P.frames, t0 = lf0 - s0 * P.frames;
+    const size_t run_row0 = (size_t)s0 * P.rows_per_stream + t0;
+    const uint32_t run_rows = min((uint32_t)n_c, P.rows_per_stream - t0);  // stay inside the first stream's rows
+    pdl_wait();  // the partial sums come from sdft_partial_kernel (K-fft in between waits for it before exiting)
+    {
+        const int n16 = (int)run_rows * G.nk;  // double2 = 16 bytes
+        const double2 *src = P.partial_c + run_row0 * G.nk;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(cs + i, src + i);
+        if (G.rem != 0) {
+            // R row of frame f is run row f + q
+            const int nr = (int)min((uint32_t)kTileFrames, P.rows_per_stream - t0 > (uint32_t)G.q ? P.rows_per_stream - t0 - G.q : 0u) * G.nk;
+            const double2 *rsrc = P.partial_r + (run_row0 + G.q) * G.nk;
+            for (int i = threadIdx.x; i < nr; i += blockDim.x) cp_async16(rs + i, rsrc + i);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (lf >= n_frames) return;
+    const uint32_t s = lf / P.frames, t = lf - s * P.frames;
+    const bool in_run = s == s0;  // same stream as the tile's first frame: rows are staged
+    const size_t row = (size_t)s * P.rows_per_stream + t;
+    for (int k = threadIdx.x & 63; k < G.nk; k += 64) {
+        double xr = 0.0, xi = 0.0;
+        if (in_run) {
+            const double2 *c = cs + (size_t)(t - t0) * G.nk + k;
+#pragma unroll 4
+            for (int i = 0; i < G.q; ++i) {
+                const double2 w = ph[i * G.nk + k];
+                const double2 v = c[(size_t)i * G.nk];
+                xr += w.x * v.x - w.y * v.y;
+                xi += w.x * v.y + w.y * v.x;
+            }
+            if (G.rem != 0) {
+                const double2 w = ph[G.q * G.nk + k];
+                const double2 v = rs[(size_t)(t - t0) * G.nk + k];
+                xr += w.x * v.x - w.y * v.y;
+                xi += w.x * v.y + w.y * v.x;
+            }
+        } else {
+            const double2 *c = P.partial_c + row * G.nk + k;
+#pragma unroll 4
+            for (int i = 0; i < G.q; ++i) {
+                const double2 w = __ldg(G.phase + i * G.nk + k);
+                const double2 v = c[(size_t)i * G.nk];
+                xr += w.x * v.x - w.y * v.y;
+                xi += w.x * v.y + w.y * v.x;
+            }
+            if (G.rem != 0) {
+                const double2 w = __ldg(G.phase + G.q * G.nk + k);
+                const double2 v = P.partial_r[(row + G.q) * G.nk + k];
+                xr += w.x * v.x - w.y * v.y;
+                xi += w.x * v.y + w.y * v.x;
+            }
+        }
+        P.spec[spec_index_re(lf, G.spec_offset + k, P.spec_stride)] = (float)xr;
+        P.spec[spec_index_im(lf, G.spec_offset + k, P.spec_stride)] = (float)xi;
+    }
+}
+
+// Benchmark hygiene: after a buffer larger than L2 has been written (the flush), reading it back leaves
+// only clean lines in L2, so the first timed kernel does not pay for writing the flush's dirty lines back.
+__global__ void __launch_bounds__(256) read_sweep_kernel(const uint4 *p, size_t n16, unsigned *sink)
+{
+    unsigned acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(p + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x9e3779b9u) *sink = acc;  // never true for a zeroed buffer; keeps the loads alive
+}
+
+}  // namespace
+
+cudaError_t launch_read_sweep(const void *p, size_t bytes, unsigned *sink, cudaStream_t stream)
+{
+    read_sweep_kernel<<<148 * 8, 256, 0, stream>>>(static_cast<const uint4 *>(p), bytes / 16, sink);
+    return cudaGetLastError();
+}
+
+size_t sdft_smem_bytes(int hop_pad) { return (size_t)kSdftRowsPerCta * hop_pad * sizeof(float); }
+size_t sdft_combine_smem_bytes(int q, int nk) { return (size_t)(2 * q + 2 * kTileFrames) * nk * sizeof(double2); }
+
+cudaError_t configure_sdft_combine(int q, int nk)
+{
+    static int configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int want = (int)sdft_combine_smem_bytes(q, nk);
+    if (want > 200 * 1024 || dev < 0 || dev >= 64) return cudaErrorInvalidConfiguration;
+    if (want <= configured[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(sdft_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) configured[dev] = want;
+    return e;
+}
+
+cudaError_t configure_sdft(int hop_pad)
+{
+    // the attribute is a per-device maximum shared by every plan (hop) of every handle: only ever raise it
+    static int configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int want = (int)sdft_smem_bytes(hop_pad);
+    if (want > 200 * 1024 || dev < 0 || dev >= 64) return cudaErrorInvalidConfiguration;
+    if (want <= configured[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(sdft_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess) configured[dev] = want;
+    return e;
+}
+
+cudaError_t launch_sdft_partial(const SdftParams &p, cudaStream_t stream)
+{
+    const uint32_t rows = p.n_streams * p.rows_per_stream;
+    const dim3 grid((rows + kSdftRowsPerCta - 1) / kSdftRowsPerCta, (p.g.nk + 63) / 64);
+    sdft_partial_kernel<<<grid, kSdftThreads, sdft_smem_bytes(p.g.hop_pad), stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream)
+{
+    const uint32_t n_frames = p.n_streams * p.frames;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n_frames + kTileFrames - 1) / kTileFrames);
+    cfg.blockDim = dim3(kTileFrames * 64);
+    cfg.dynamicSmemBytes = sdft_combine_smem_bytes(p.g.q, p.g.nk);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, sdft_combine_kernel, p);
+}
+
+}  // namespace pvqt_dev

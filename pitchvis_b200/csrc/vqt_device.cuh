@@ -63,7 +63,50 @@ struct FftParams {
     int32_t     spec_stride;  // columns per tile (multiple of 8)
     FrameLayout frames;
     float      *spec;         // tiled planar layout, ceil(n_frames / 8) tiles
+    int32_t     wait_prior;   // 1: launched programmatically behind K-sdft, wait for it before exiting
 };
+
+// Sliding partial-DFT path of one window group ("K-sdft").  When consecutive frames overlap (hop H much
+// smaller than the window N) and the sparse kernel consumes only a few low bins of the group's FFT,
+// the consumed bins are cheaper as sums of hop-sized partial DFTs that neighbouring frames share:
+//   N = q H + rem,   X_t[k] = sum_{i<q} e^{-2 pi i k i H / N} C[t+i][k] + e^{-2 pi i k q H / N} R[t+q][k]
+//   C[c][k] = sum_{j<H}   x[c H + window_begin + j] e^{-2 pi i k j / N}     (one chunk, computed once)
+//   R[c][k] = sum_{j<rem} x[c H + window_begin + j] e^{-2 pi i k j / N}     (prefix of the same sum)
+// Same unnormalised forward DFT as the FFT path (vqt.rs:884-887 / :1087-1128), evaluated in another
+// order; each sample is read once instead of q times.  The chunk twiddle is split in two levels,
+// e^{-2 pi i k (16 a + b) / N} = A[a][k] B[b][k], so the 16 B's stay in registers.
+struct SdftGroup {
+    int32_t window_begin;   // first sample of the window inside an n_fft frame
+    int32_t n_window;       // N
+    int32_t k_lo, nk;       // consumed bins k_lo .. k_lo + nk - 1
+    int32_t spec_offset;    // position of k_lo inside a frame's spectrum row
+    int32_t hop, q, rem;    // N = q * hop + rem
+    int32_t n_blocks;       // ceil(hop / 16)
+    int32_t hop_pad;        // 16 * n_blocks
+    const float2 *tw_a;     // [n_blocks][nk]
+    const float2 *tw_b;     // [16][nk]
+    const double2 *phase;   // [q + 1][nk], f64 (the combine runs in f64)
+};
+
+struct SdftParams {
+    SdftGroup    g;
+    const float *audio;
+    uint64_t     stream_stride;
+    uint64_t     valid_samples;    // samples every stream holds: (frames_per_stream - 1) * hop + n_fft
+    uint32_t     first_stream;     // streams [first_stream, first_stream + n_streams) ...
+    uint32_t     n_streams;
+    uint32_t     first_frame;      // ... frames [first_frame, first_frame + frames) of each
+    uint32_t     frames;
+    uint32_t     rows_per_stream;  // chunk rows per stream: frames + q
+    int32_t      spec_stride;
+    double2     *partial_c;        // [n_streams * rows_per_stream][nk], f64 (see sdft_partial_kernel)
+    double2     *partial_r;
+    float       *spec;             // tiled planar layout; local frame = stream_local * frames + t
+};
+
+constexpr int kSdftThreads = 256;     // 4 row groups x 2 bin halves (64 bins per CTA)
+constexpr int kSdftRowsPerWarp = 4;   // chunk rows a lane accumulates concurrently
+constexpr int kSdftRowsPerCta = 16;   // few, fat CTAs: all resident at once, so K-fft can start beside them
 
 // The spectral kernel as the SpMM sees it: blocks of 64 consecutive rows of one window group, two
 // adjacent rows per lane.  A lane's two rows share one zero-filled band of columns
@@ -103,12 +146,51 @@ struct DbParams {
     float    ref_db;           // 10 * log10(0.3 * 0.3), vqt.rs:923,927
 };
 
+// Fused K-spmm-db: one CTA per 8-frame tile owns every kernel row, so power_to_db's frame-wise
+// max / min never leave the SM.  The row pairs ("units") are sorted by band length and dealt to
+// warps, so the lanes of a warp run (almost) the same number of band slots; inside a warp the units
+// are placed so that the spectrum records of a quarter-warp fall on distinct bank groups.
+struct FusedWarp {
+    int32_t width;       // band slots the warp walks (the longest unit of the warp)
+    int32_t nwidth;      // conjugate-part slots
+    int32_t val_base;    // first slot in `values` (slot = 32 float4)
+    int32_t nval_base;
+};
+
+struct FusedParams {
+    const FusedWarp *warps;
+    const int4   *lane_meta;   // [warp][lane]: (col0, len, ncol0, nlen) in spectrum columns
+    const int2   *lane_rows;   // [warp][lane]: (first output row, valid rows 0..2)
+    const float4 *values;      // [slot][lane]: (K[row0].re, K[row0].im, K[row1].re, K[row1].im)
+    int32_t  n_warps;
+    int32_t  n_buckets;
+    int32_t  spec_stride;      // columns per tile
+    int32_t  n_cols;           // columns staged per tile (<= spec_stride)
+    uint32_t n_frames;
+    uint32_t n_tiles;
+    const float *spec;         // tiled planar layout
+    float   *out_db;           // [n_frames][n_buckets]
+    float   *power;            // optional [n_frames][n_buckets]
+    float    ref_db;
+};
+
 constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
 constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
 
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream);
+cudaError_t launch_sdft_partial(const SdftParams &p, cudaStream_t stream);
+cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream);
+cudaError_t configure_sdft(int hop_pad);
+cudaError_t configure_sdft_combine(int q, int nk);
+size_t sdft_combine_smem_bytes(int q, int nk);
+cudaError_t launch_read_sweep(const void *p, size_t bytes, unsigned *sink, cudaStream_t stream);
+size_t sdft_smem_bytes(int hop_pad);
 cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream);
 cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream);
+cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream);
+bool        fused_supported(int n_warps, int n_cols, int n_buckets);
+size_t      fused_smem_bytes(int n_cols, int n_buckets);
+cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets);
 cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);
 size_t spmm_smem_bytes(int max_cols);

@@ -16,32 +16,14 @@
 // FFT convention (pinned by vqt.rs:1087-1128): unnormalised forward transform,
 // X[k] = sum_n x[n] exp(-2 pi i k n / N), half spectrum k = 0..N/2.
 #include "vqt_device.cuh"
+#include "device_helpers.cuh"
+
+#include <algorithm>
 
 #include <math_constants.h>
 
 namespace pvqt_dev {
 namespace {
-
-// Programmatic dependent launch: K-spmm and K-db are launched with the programmatic-stream-
-// serialization attribute, so their CTAs may become resident while the producer kernel drains.
-// pdl_wait() blocks until the producer grid has completed and its writes are visible;
-// pdl_launch_dependents() lets the next kernel in the stream start its prologue.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" :::); }
-
-// ------------------------------------------------------------------------------------------
-// packed complex helpers (float2 = one 64-bit register pair)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
-// a * (-i): a swap + partial negation, folded by ptxas into the consumer's operand modifiers
-__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
-// a * w:  t = w.y * (a.y, a.x);  result = w.x * a + (-t.x, t.y)          (FMUL2 + FFMA2)
-__device__ __forceinline__ float2 cmul(float2 a, float2 w)
-{
-    const float2 t = __fmul2_rn(make_float2(w.y, w.y), make_float2(a.y, a.x));
-    return __ffma2_rn(make_float2(w.x, w.x), a, make_float2(-t.x, t.y));
-}
 
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 constexpr float kCosPi8 = 0.92387953251128675613f;
@@ -331,22 +313,14 @@ __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant
 #undef PVQT_FFT_CASE
     default: break;
     }
+    // Launched programmatically behind K-sdft (which runs beside this kernel): do not complete before it
+    // has, so that the kernels after this one see the partial sums too.
+    if (P.wait_prior) pdl_wait();
 }
 
 // ------------------------------------------------------------------------------------------
 // K-spmm: banded complex SpMM, kernel-stationary
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group 0;\n" ::);
-}
-
 // One kernel coefficient k applied to the 8 frames of one spectrum record.  Accumulators are planar
 // frame pairs: re[p] = (Re y_f2p, Re y_f2p+1), im[p] likewise; xr* / xi* are the record's chunks.
 //   y += k x:        re += k.re xr - k.im xi,   im += k.re xi + k.im xr          (vqt.rs:889-894)
@@ -546,6 +520,142 @@ __global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K-spmm-db: banded complex SpMM + |z|^2 + power_to_db, one CTA per 8-frame tile
+// ------------------------------------------------------------------------------------------
+// The CTA stages the tile's whole spectrum (n_cols 64-byte records) once, every lane accumulates its
+// two kernel rows for the 8 frames (same arithmetic and summation order as spmm_kernel), and because
+// the CTA owns all n_buckets rows of its frames the frame-wise max / min of power_to_db (vqt.rs:933-940)
+// are reduced in shared memory: the dB values are written once, coalesced, and the |z|^2 round trip
+// through HBM/L2 and the third launch disappear.
+template <int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(const __grid_constant__ FusedParams P)
+{
+    extern __shared__ __align__(16) float4 fused_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x;
+    const FusedWarp W = P.warps[warp];
+    const int4 meta = __ldg(P.lane_meta + warp * 32 + lane);
+    const int2 rows = __ldg(P.lane_rows + warp * 32 + lane);
+    const float4 *kv = P.values + (size_t)W.val_base * 32 + lane;
+    const float4 *nv = P.values + (size_t)W.nval_base * 32 + lane;
+    float4 kq = __ldg(kv);  // `values` ends with spare slots: the prefetch below may overrun by one
+
+    pdl_launch_dependents();
+    pdl_wait();  // everything above is plan data; the spectra below come from K-fft / K-sdft
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(P.spec) + (size_t)tile * P.spec_stride * 4;
+        const int n16 = P.n_cols * 4;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(fused_smem + i, src + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    float2 re0[4], im0[4], re1[4], im1[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) re0[p] = im0[p] = re1[p] = im1[p] = make_float2(0.f, 0.f);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+    for (int j = 0; j < W.width; ++j) {
+        const float4 k = kq;
+        kq = __ldg(kv + (j + 1) * 32);
+        const int c = meta.x + j;
+        const float4 *rec = fused_smem + c * 4;
+        const int sw = (c >> 1) & 3;
+        float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
+        if (j < meta.y) {
+            xr03 = rec[sw];
+            xr47 = rec[1 ^ sw];
+            xi03 = rec[2 ^ sw];
+            xi47 = rec[3 ^ sw];
+        }
+        mac8<false>(re0, im0, k.x, k.y, xr03, xr47, xi03, xi47);
+        mac8<false>(re1, im1, k.z, k.w, xr03, xr47, xi03, xi47);
+    }
+    for (int j = 0; j < W.nwidth; ++j) {
+        const float4 k = __ldg(nv + j * 32);  // conj(Kneg), see device plan
+        const int c = meta.z + j;
+        const float4 *rec = fused_smem + c * 4;
+        const int sw = (c >> 1) & 3;
+        float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
+        if (j < meta.w) {
+            xr03 = rec[sw];
+            xr47 = rec[1 ^ sw];
+            xi03 = rec[2 ^ sw];
+            xi47 = rec[3 ^ sw];
+        }
+        mac8<true>(re0, im0, k.x, k.y, xr03, xr47, xi03, xi47);
+        mac8<true>(re1, im1, k.z, k.w, xr03, xr47, xi03, xi47);
+    }
+
+    // |z|^2 (norm_sqr) and log_spec (vqt.rs:930) per lane; the staging buffer becomes ls[frame][row]
+    const float pr0[kTileFrames] = {re0[0].x, re0[0].y, re0[1].x, re0[1].y, re0[2].x, re0[2].y, re0[3].x, re0[3].y};
+    const float pi0[kTileFrames] = {im0[0].x, im0[0].y, im0[1].x, im0[1].y, im0[2].x, im0[2].y, im0[3].x, im0[3].y};
+    const float pr1[kTileFrames] = {re1[0].x, re1[0].y, re1[1].x, re1[1].y, re1[2].x, re1[2].y, re1[3].x, re1[3].y};
+    const float pi1[kTileFrames] = {im1[0].x, im1[0].y, im1[1].x, im1[1].y, im1[2].x, im1[2].y, im1[3].x, im1[3].y};
+    const uint32_t frame0 = tile * kTileFrames;
+    const int nb = P.n_buckets;
+    __syncthreads();  // every warp is done reading the staged spectrum
+    float *ls = reinterpret_cast<float *>(fused_smem);
+#pragma unroll
+    for (int f = 0; f < kTileFrames; ++f) {
+        const float p0 = pr0[f] * pr0[f] + pi0[f] * pi0[f];
+        const float p1 = pr1[f] * pr1[f] + pi1[f] * pi1[f];
+        if (rows.y > 0) ls[f * nb + rows.x] = log_spec(p0, P.ref_db);
+        if (rows.y > 1) ls[f * nb + rows.x + 1] = log_spec(p1, P.ref_db);
+        if (P.power != nullptr && frame0 + f < P.n_frames) {
+            float *pw = P.power + (size_t)(frame0 + f) * nb + rows.x;
+            if (rows.y > 0) pw[0] = p0;
+            if (rows.y > 1) pw[1] = p1;
+        }
+    }
+    __syncthreads();
+
+    // power_to_db's frame-wise part (vqt.rs:933-950): one warp per frame, coalesced stores
+    const int n_warps = blockDim.x >> 5;
+    for (int f = warp; f < kTileFrames; f += n_warps) {
+        if (frame0 + f >= P.n_frames) break;
+        const float *l = ls + f * nb;
+        float *out = P.out_db + (size_t)(frame0 + f) * nb;
+        float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+        const bool vec = (nb & 3) == 0 && (reinterpret_cast<uintptr_t>(P.out_db) & 15) == 0;
+        if (vec) {
+            const float4 *l4 = reinterpret_cast<const float4 *>(l);
+            const int n4 = nb >> 2;
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = l4[i];
+                mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+                mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+            }
+        } else {
+            for (int r = lane; r < nb; r += 32) {
+                mx = fmaxf(mx, l[r]);
+                mn = fminf(mn, l[r]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        const float floor_db = mx - kTopDb, log_spec_min = fmaxf(mn, floor_db);  // vqt.rs:939-940
+        if (vec) {
+            const float4 *l4 = reinterpret_cast<const float4 *>(l);
+            float4 *o4 = reinterpret_cast<float4 *>(out);
+            const int n4 = nb >> 2;
+            for (int i = lane; i < n4; i += 32) {
+                const float4 v = l4[i];
+                o4[i] = make_float4(db_out(v.x, floor_db, log_spec_min), db_out(v.y, floor_db, log_spec_min),
+                                    db_out(v.z, floor_db, log_spec_min), db_out(v.w, floor_db, log_spec_min));
+            }
+        } else {
+            for (int r = lane; r < nb; r += 32) out[r] = db_out(l[r], floor_db, log_spec_min);
+        }
+    }
+}
+
 }  // namespace
 
 size_t fft_smem_bytes(int block_threads)
@@ -570,18 +680,6 @@ cudaError_t configure_kernels(int max_cols)
                                 (int)spmm_smem_bytes(max_cols));
 }
 
-cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream)
-{
-    const size_t smem = fft_smem_bytes(block_threads);
-    switch (block_threads) {
-    case 256: fft_groups_kernel<256><<<total_ctas, 256, smem, stream>>>(p); break;
-    case 512: fft_groups_kernel<512><<<total_ctas, 512, smem, stream>>>(p); break;
-    case 1024: fft_groups_kernel<1024><<<total_ctas, 1024, smem, stream>>>(p); break;
-    default: return cudaErrorInvalidConfiguration;
-    }
-    return cudaGetLastError();
-}
-
 namespace {
 template <typename Kernel, typename Params>
 cudaError_t launch_dependent(Kernel kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
@@ -601,10 +699,70 @@ cudaError_t launch_dependent(Kernel kernel, unsigned grid, unsigned block, size_
 }
 }  // namespace
 
+cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream)
+{
+    const size_t smem = fft_smem_bytes(block_threads);
+    if (p.wait_prior) {
+        switch (block_threads) {
+        case 256: return launch_dependent(fft_groups_kernel<256>, total_ctas, 256, smem, stream, p);
+        case 512: return launch_dependent(fft_groups_kernel<512>, total_ctas, 512, smem, stream, p);
+        case 1024: return launch_dependent(fft_groups_kernel<1024>, total_ctas, 1024, smem, stream, p);
+        default: return cudaErrorInvalidConfiguration;
+        }
+    }
+    switch (block_threads) {
+    case 256: fft_groups_kernel<256><<<total_ctas, 256, smem, stream>>>(p); break;
+    case 512: fft_groups_kernel<512><<<total_ctas, 512, smem, stream>>>(p); break;
+    case 1024: fft_groups_kernel<1024><<<total_ctas, 1024, smem, stream>>>(p); break;
+    default: return cudaErrorInvalidConfiguration;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream)
 {
     const unsigned tile_groups = (p.n_tiles + kSpmmWarps - 1) / kSpmmWarps;
     return launch_dependent(spmm_kernel, tile_groups * p.n_blocks, kSpmmWarps * 32, spmm_smem_bytes(p.max_cols), stream, p);
+}
+
+// ---- K-spmm-db launch -------------------------------------------------------------------------
+size_t fused_smem_bytes(int n_cols, int n_buckets)
+{
+    const size_t stage = (size_t)n_cols * kTileFrames * sizeof(float2);
+    const size_t ls = (size_t)kTileFrames * n_buckets * sizeof(float);
+    return (std::max(stage, ls) + 15) & ~(size_t)15;
+}
+
+bool fused_supported(int n_warps, int n_cols, int n_buckets)
+{
+    return n_warps >= 1 && n_warps <= 32 && fused_smem_bytes(n_cols, n_buckets) <= 200 * 1024;
+}
+
+namespace {
+template <typename Fn>
+cudaError_t with_fused_kernel(int n_warps, Fn fn)
+{
+    // register budget: 3 resident CTAs of <= 10 warps (64 registers), 2 of <= 16, 1 beyond
+    if (n_warps <= 10) return fn(spmm_db_fused_kernel<320, 3>);
+    if (n_warps <= 16) return fn(spmm_db_fused_kernel<512, 2>);
+    return fn(spmm_db_fused_kernel<1024, 1>);
+}
+}  // namespace
+
+cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets)
+{
+    const int smem = (int)fused_smem_bytes(n_cols, n_buckets);
+    return with_fused_kernel(n_warps, [&](auto kernel) {
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    });
+}
+
+cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream)
+{
+    const size_t smem = fused_smem_bytes(p.n_cols, p.n_buckets);
+    return with_fused_kernel(p.n_warps, [&](auto kernel) {
+        return launch_dependent(kernel, p.n_tiles, (unsigned)p.n_warps * 32, smem, stream, p);
+    });
 }
 
 cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream)

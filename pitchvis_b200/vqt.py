@@ -232,6 +232,14 @@ class Vqt:
     def launch_count(self) -> int:
         return int(self._lib.pvqt_launch_count(self._h))
 
+    def set_fused_epilogue(self, enabled: bool) -> bool:
+        """Tuning / test switch: False forces the unfused K-spmm + K-db pair.  Returns the value in effect."""
+        return bool(self._lib.pvqt_set_fused_epilogue(self._h, 1 if enabled else 0))
+
+    def set_sliding_dft(self, enabled: bool) -> bool:
+        """Tuning / test switch: False keeps every window group on the per-frame FFT path in batched calls."""
+        return bool(self._lib.pvqt_set_sliding_dft(self._h, 1 if enabled else 0))
+
     # ---- per-frame entry point (vqt.rs:866) ----------------------------------------------
     def calculate_vqt_instant_in_db(self, x) -> np.ndarray:
         x = _as_f32(x, "x")

@@ -160,21 +160,98 @@ def test_power_parity_above_minus_80_db(vqt, oracle_default, chords):
     assert np.abs(db_gpu - db_from_pow).max() <= 2e-5
 
 
+def test_fused_epilogue_matches_unfused_pair(vqt, chords):
+    # K-spmm-db (one CTA per tile owns all rows, dB fused) against K-spmm + K-db: same sums, same order
+    n_frames = 77  # not a multiple of the 8-frame tile
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_audio.upload(audio)
+    res = {}
+    try:
+        for fused in (True, False):
+            assert vqt.set_fused_epilogue(fused) == fused
+            d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+            d_pow = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+            pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, d_pow)
+            res[fused] = (d_out.download((n_frames, 588)), d_pow.download((n_frames, 588)))
+            pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, None)  # without the optional power output
+            np.testing.assert_array_equal(d_out.download((n_frames, 588)), res[fused][0])
+    finally:
+        vqt.set_fused_epilogue(True)
+    np.testing.assert_array_equal(res[True][1], res[False][1])
+    np.testing.assert_array_equal(res[True][0], res[False][0])
+
+
 def test_frames_streams_and_instant_are_bit_identical(vqt, chords):
     n_frames = 40
     audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
-    batch = vqt.calculate_vqt_batch_in_db(audio, HOP)
     frames = np.stack([audio[t * HOP:t * HOP + vqt.n_fft] for t in range(n_frames)])
-    np.testing.assert_array_equal(vqt.calculate_vqt_frames_in_db(frames), batch)
-    for t in (0, 17, n_frames - 1):
-        np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(frames[t]), batch[t])
-    # streams: 3 recordings of different content, each equals its own batch call
     n = vqt.n_fft + 9 * HOP
     streams = np.stack([chords[o:o + n] for o in (0, 5000, 12345)])
-    out = vqt.calculate_vqt_streams_in_db(streams, HOP)
-    assert out.shape == (3, 10, 588)
+    try:
+        # every window group on the per-frame FFT path: all entry points run the same arithmetic
+        vqt.set_sliding_dft(False)
+        batch = vqt.calculate_vqt_batch_in_db(audio, HOP)
+        np.testing.assert_array_equal(vqt.calculate_vqt_frames_in_db(frames), batch)
+        for t in (0, 17, n_frames - 1):
+            np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(frames[t]), batch[t])
+        # streams: 3 recordings of different content, each equals its own batch call
+        out = vqt.calculate_vqt_streams_in_db(streams, HOP)
+        assert out.shape == (3, 10, 588)
+        for s in range(3):
+            np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+    finally:
+        vqt.set_sliding_dft(True)
+    # default: overlapping frames take the sliding partial-DFT path for group 0 (same DFT, other summation
+    # order), the independent-frames entries keep the FFT -- equal within the parity tolerance
+    sliding = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    assert np.abs(sliding - batch).max() <= TOL_DB
+    assert np.abs(vqt.calculate_vqt_frames_in_db(frames) - sliding).max() <= TOL_DB
+
+
+def test_sliding_dft_path(vqt, oracle_default, chords):
+    """K-sdft (group 0's 61 consumed bins as sums of hop-sized partial DFTs) against numpy's f64 rfft, against
+    the FFT path, and end to end against the oracle; launch boundaries and stream boundaries included."""
+    n_frames = 150
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_audio.upload(audio)
+    stride = vqt.spec_stride
+    n_tiles = (n_frames + 7) // 8
+    d_spec = pv.DeviceBuffer(vqt, n_tiles * stride * 8 * 8)
+    launches = vqt.launch_count
+    pv.fft_device(vqt, d_audio, 1, 0, HOP, n_frames, d_spec)
+    assert vqt.launch_count - launches == 3          # partial sums, FFT of the other groups, combine
+    spec = _untile_spec(d_spec.download((n_tiles, stride, 16), np.float32), n_frames, stride)
+    wg = vqt.kernel().window_groups[0]
+    first, n_cols, off = vqt.group_columns(0)
+    wb, we = wg.window
+    worst = 0.0
+    for t in (0, 1, 7, 8, 63, 149):
+        full = np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))
+        got = spec[t, off:off + n_cols].astype(np.complex128)
+        worst = max(worst, np.abs(got - full[first:first + n_cols]).max() / np.abs(full).max())
+    assert worst <= 5e-7, worst
+    # end to end, several streams (chunk rows of different streams share CTAs)
+    n = vqt.n_fft + 39 * HOP
+    streams = np.stack([chords[o:o + n] for o in (0, 7001, 20000)])
+    got = vqt.calculate_vqt_streams_in_db(streams, HOP)
     for s in range(3):
-        np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+        ref = oracle_default.calculate_batch_db(streams[s], HOP, mode=0)
+        assert np.abs(got[s] - ref).max() <= TOL_DB
+        np.testing.assert_array_equal(got[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+    # a hop that is not a multiple of 16 and leaves a remainder that ends inside a 16-sample block
+    hop = 333
+    nf = 60
+    a2 = chords[1000:1000 + vqt.n_fft + (nf - 1) * hop]
+    got2 = vqt.calculate_vqt_batch_in_db(a2, hop)
+    ref2 = oracle_default.calculate_batch_db(a2, hop, mode=0)
+    assert np.abs(got2 - ref2).max() <= TOL_DB
+    try:
+        vqt.set_sliding_dft(False)
+        assert np.abs(vqt.calculate_vqt_batch_in_db(a2, hop) - got2).max() <= TOL_DB
+    finally:
+        vqt.set_sliding_dft(True)
 
 
 def test_edge_cases(vqt):
@@ -239,8 +316,10 @@ def test_linearity_property_full_size(vqt):
     # host-buffer entry == device-resident entry, bit for bit
     np.testing.assert_array_equal(vqt.calculate_vqt_batch_in_db(audio, HOP), db1)
     # a frame of the long run equals the per-frame entry point on the same samples
+    # a frame of the long run against the per-frame entry point on the same samples (FFT path for every group)
     for t in (0, 1234, 3506):
-        np.testing.assert_array_equal(vqt.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft]), db1[t])
+        one = vqt.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft])
+        assert np.abs(one - db1[t]).max() <= TOL_DB
 
 
 def test_hires_config(built_lib):
