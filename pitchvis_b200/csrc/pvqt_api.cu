@@ -546,17 +546,12 @@ const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
             const double a = -2.0 * kPi * (double)r / (double)n;
             return make_float2((float)std::cos(a), (float)std::sin(a));
         };
-        std::vector<float2> ta((size_t)g.n_blocks * nk), tb((size_t)16 * nk);
-        std::vector<double2> ph((size_t)(g.q + 1) * nk);
+        std::vector<float2> ta((size_t)g.n_blocks * nk), tb((size_t)16 * nk), ph((size_t)(g.q + 1) * nk);
         for (size_t k = 0; k < nk; ++k) {
             const uint64_t ka = g.k_lo + k;
             for (int a = 0; a < g.n_blocks; ++a) ta[(size_t)a * nk + k] = tw(ka, 16ull * a);
             for (int b = 0; b < 16; ++b) tb[(size_t)b * nk + k] = tw(ka, b);
-            for (int i = 0; i <= g.q; ++i) {
-                const uint64_t r = (ka * (uint64_t)i * hop) % n;
-                const double a = -2.0 * kPi * (double)r / (double)n;
-                ph[(size_t)i * nk + k] = make_double2(std::cos(a), std::sin(a));
-            }
+            for (int i = 0; i <= g.q; ++i) ph[(size_t)i * nk + k] = tw(ka, (uint64_t)i * hop);
         }
         cudaError_t e;
         if ((e = upload(v, ta, &g.tw_a)) != cudaSuccess || (e = upload(v, tb, &g.tw_b)) != cudaSuccess ||
@@ -636,7 +631,8 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
         if (st != PVQT_OK) return st;
         if (plan)
             for (size_t i = 0; i < plan->groups.size(); ++i)
-                if (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream))
+                if ((int)sdft_groups.size() < kMaxSdft &&
+                    sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream))
                     sdft_groups.push_back((int)i);
     }
     auto on_sdft = [&](int gi) {
@@ -674,14 +670,14 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             }
             if (!sd.empty()) {
                 size_t need = 0;
-                for (const auto &sp : sd) need += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(double2);
+                for (const auto &sp : sd) need += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                 if (v->sdft_c.reserve(need) != cudaSuccess || v->sdft_r.reserve(need) != cudaSuccess)
                     return cuda_fail(cudaGetLastError(), "allocate K-sdft scratch");
                 size_t off = 0;
                 for (auto &sp : sd) {
-                    sp.partial_c = reinterpret_cast<double2 *>(static_cast<char *>(v->sdft_c.ptr) + off);
-                    sp.partial_r = reinterpret_cast<double2 *>(static_cast<char *>(v->sdft_r.ptr) + off);
-                    off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(double2);
+                    sp.partial_c = reinterpret_cast<float2 *>(static_cast<char *>(v->sdft_c.ptr) + off);
+                    sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(v->sdft_r.ptr) + off);
+                    off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                     prof_begin(v, 4, stream);
                     cudaError_t e = launch_sdft_partial(sp, stream);
                     if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
@@ -709,7 +705,10 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 ++kept;
             }
             fp.n_groups = kept;
+            fp.n_sdft = 0;
             if (kept > 0) {
+                for (const auto &sp : sd) fp.sdft[fp.n_sdft++] = sp;
+                fp.combine_group = kept - 1;  // the last group: its CTAs start when the partial sums are long complete
                 prof_begin(v, 0, stream);
                 cudaError_t e = launch_fft(fp, ctas, v->fft_block_threads, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "launch fft_groups_kernel");
@@ -717,14 +716,15 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 v->launches.fetch_add(1);
             }
 
-            // ---- K-sdft combine: the sliding groups' bins join the FFT groups' in the spectrum tiles ----
-            for (const auto &sp : sd) {
-                prof_begin(v, 5, stream);
-                cudaError_t e = launch_sdft_combine(sp, stream);
-                if (e != cudaSuccess) return cuda_fail(e, "launch sdft_combine_kernel");
-                prof_end(v, stream);
-                v->launches.fetch_add(1);
-            }
+            // ---- K-sdft combine: run by K-fft's last CTAs; its own launch only when no FFT group is left ----
+            if (kept == 0)
+                for (const auto &sp : sd) {
+                    prof_begin(v, 5, stream);
+                    cudaError_t e = launch_sdft_combine(sp, stream);
+                    if (e != cudaSuccess) return cuda_fail(e, "launch sdft_combine_kernel");
+                    prof_end(v, stream);
+                    v->launches.fetch_add(1);
+                }
             if (d_spec_out) continue;
 
             cudaError_t e;

@@ -9,6 +9,7 @@
 // Replaces, for the groups it is selected for, the realfft call of vqt.rs:884-887: same unnormalised
 // forward DFT, X[k] = sum_n x[n] exp(-2 pi i k n / N), summed chunk by chunk in f32.
 #include "device_helpers.cuh"
+#include "sdft_combine.cuh"
 #include "vqt_device.cuh"
 
 namespace pvqt_dev {
@@ -26,7 +27,7 @@ __device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gmem
 // block the packed FFMA2 lanes hold the even / odd samples' contributions -- both operands are natural
 // register pairs: two consecutive samples of one LDS.128 and the matching pair of B twiddles -- added at
 // the end of the block, times A[a], into the chunk's running sum.  All f32; the long sum over chunks is
-// done in f64 by the combine step, which is where the accuracy of the path is decided.
+// compensated (Kahan) in the combine step, which is where the accuracy of the path is decided.
 __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __grid_constant__ SdftParams P)
 {
     extern __shared__ __align__(16) float4 sdft_smem[];
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __g
                 }
                 const float2 r = cadd(acc[ch], cmul(sp, A));
                 const uint32_t row = my_row0 + ch;
-                if (active && row < total_rows) P.partial_r[(size_t)row * G.nk + k] = make_double2((double)r.x, (double)r.y);
+                if (active && row < total_rows) P.partial_r[(size_t)row * G.nk + k] = r;
             }
         }
         float2 sre[kSdftRowsPerWarp], sim[kSdftRowsPerWarp];
@@ -135,87 +136,19 @@ __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __g
         for (int ch = 0; ch < kSdftRowsPerWarp; ++ch) {
             const uint32_t row = my_row0 + ch;
             if (row < total_rows)
-                P.partial_c[(size_t)row * G.nk + k] = make_double2((double)acc[ch].x, (double)acc[ch].y);
+                P.partial_c[(size_t)row * G.nk + k] = acc[ch];
         }
     }
 }
 
-// One CTA per 8-frame tile: the q + 8 chunk rows the tile's frames need are staged once (cp.async), then
-// thread (frame, bin) sums its q (+1) rows in f64 (the rounding of this long sum is what limits the
-// accuracy of the path: in f32 it costs 4x the error).
+// Stand-alone combine (one CTA per 8-frame tile); used when no K-fft launch follows the partial sums.
 __global__ void __launch_bounds__(kTileFrames * 64) sdft_combine_kernel(const __grid_constant__ SdftParams P)
 {
-    extern __shared__ __align__(16) double2 comb_smem[];   // [q + 7 rows][nk] C, [8][nk] R, [q + 1][nk] phase
-    const SdftGroup &G = P.g;
+    extern __shared__ __align__(16) float2 comb_smem[];
     pdl_launch_dependents();
-    const uint32_t n_frames = P.n_streams * P.frames;
-    const uint32_t lf0 = blockIdx.x * kTileFrames;
-    const int fi = threadIdx.x >> 6;
-    const uint32_t lf = lf0 + fi;
-    const int n_c = G.q + kTileFrames - 1;  // C rows per frame-aligned run; R rows: one per frame
-    double2 *cs = comb_smem, *rs = comb_smem + (size_t)n_c * G.nk, *ph = rs + (size_t)kTileFrames * G.nk;
-    for (int i = threadIdx.x; i < (G.q + 1) * G.nk; i += blockDim.x) cp_async16(ph + i, G.phase + i);  // plan data
-    // Frames of a tile may straddle two streams: stage per frame-row with the row index computed per frame.
-    // Row of (frame f, i): stream(f) * rows_per_stream + t(f) + i.  For frames of one stream the rows of
-    // consecutive frames overlap; stage the run [row(first frame), + q + 7) and let other streams' frames
-    // (rare: only at stream boundaries) read global memory directly.
-    const uint32_t s0 = lf0 / P.frames, t0 = lf0 - s0 * P.frames;
-    const size_t run_row0 = (size_t)s0 * P.rows_per_stream + t0;
-    const uint32_t run_rows = min((uint32_t)n_c, P.rows_per_stream - t0);  // stay inside the first stream's rows
-    pdl_wait();  // the partial sums come from sdft_partial_kernel (K-fft in between waits for it before exiting)
-    {
-        const int n16 = (int)run_rows * G.nk;  // double2 = 16 bytes
-        const double2 *src = P.partial_c + run_row0 * G.nk;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(cs + i, src + i);
-        if (G.rem != 0) {
-            // R row of frame f is run row f + q
-            const int nr = (int)min((uint32_t)kTileFrames, P.rows_per_stream - t0 > (uint32_t)G.q ? P.rows_per_stream - t0 - G.q : 0u) * G.nk;
-            const double2 *rsrc = P.partial_r + (run_row0 + G.q) * G.nk;
-            for (int i = threadIdx.x; i < nr; i += blockDim.x) cp_async16(rs + i, rsrc + i);
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    if (lf >= n_frames) return;
-    const uint32_t s = lf / P.frames, t = lf - s * P.frames;
-    const bool in_run = s == s0;  // same stream as the tile's first frame: rows are staged
-    const size_t row = (size_t)s * P.rows_per_stream + t;
-    for (int k = threadIdx.x & 63; k < G.nk; k += 64) {
-        double xr = 0.0, xi = 0.0;
-        if (in_run) {
-            const double2 *c = cs + (size_t)(t - t0) * G.nk + k;
-#pragma unroll 4
-            for (int i = 0; i < G.q; ++i) {
-                const double2 w = ph[i * G.nk + k];
-                const double2 v = c[(size_t)i * G.nk];
-                xr += w.x * v.x - w.y * v.y;
-                xi += w.x * v.y + w.y * v.x;
-            }
-            if (G.rem != 0) {
-                const double2 w = ph[G.q * G.nk + k];
-                const double2 v = rs[(size_t)(t - t0) * G.nk + k];
-                xr += w.x * v.x - w.y * v.y;
-                xi += w.x * v.y + w.y * v.x;
-            }
-        } else {
-            const double2 *c = P.partial_c + row * G.nk + k;
-#pragma unroll 4
-            for (int i = 0; i < G.q; ++i) {
-                const double2 w = __ldg(G.phase + i * G.nk + k);
-                const double2 v = c[(size_t)i * G.nk];
-                xr += w.x * v.x - w.y * v.y;
-                xi += w.x * v.y + w.y * v.x;
-            }
-            if (G.rem != 0) {
-                const double2 w = __ldg(G.phase + G.q * G.nk + k);
-                const double2 v = P.partial_r[(row + G.q) * G.nk + k];
-                xr += w.x * v.x - w.y * v.y;
-                xi += w.x * v.y + w.y * v.x;
-            }
-        }
-        P.spec[spec_index_re(lf, G.spec_offset + k, P.spec_stride)] = (float)xr;
-        P.spec[spec_index_im(lf, G.spec_offset + k, P.spec_stride)] = (float)xi;
-    }
+    pdl_wait();  // the partial sums come from sdft_partial_kernel
+    sdft_combine_frames(P, blockIdx.x * kTileFrames, kTileFrames, comb_smem,
+                        sdft_combine_smem_bytes_dev(P.g.q, P.g.nk));
 }
 
 // Benchmark hygiene: after a buffer larger than L2 has been written (the flush), reading it back leaves
@@ -239,7 +172,7 @@ cudaError_t launch_read_sweep(const void *p, size_t bytes, unsigned *sink, cudaS
 }
 
 size_t sdft_smem_bytes(int hop_pad) { return (size_t)kSdftRowsPerCta * hop_pad * sizeof(float); }
-size_t sdft_combine_smem_bytes(int q, int nk) { return (size_t)(2 * q + 2 * kTileFrames) * nk * sizeof(double2); }
+size_t sdft_combine_smem_bytes(int q, int nk) { return sdft_combine_smem_bytes_dev(q, nk); }
 
 cudaError_t configure_sdft_combine(int q, int nk)
 {

@@ -7,6 +7,7 @@
 namespace pvqt_dev {
 
 constexpr int kMaxGroups = 8;          // window groups per Vqt (4 at the defaults, 5 hi-res)
+constexpr int kMaxSdft = 2;            // window groups on the sliding partial-DFT path per launch
 constexpr int kMaxFftPasses = 4;       // radix passes of the largest plan (N_c = 16384)
 constexpr int kPointsPerThread = 16;   // complex points each FFT thread keeps in registers
 constexpr int kTileFrames = 8;         // frames per spectrum tile (one 64-byte record per column)
@@ -57,15 +58,6 @@ struct FrameLayout {
     uint64_t first_frame;     // global index of local frame 0 (for addressing `audio`)
 };
 
-struct FftParams {
-    FftGroup    group[kMaxGroups];
-    int32_t     n_groups;
-    int32_t     spec_stride;  // columns per tile (multiple of 8)
-    FrameLayout frames;
-    float      *spec;         // tiled planar layout, ceil(n_frames / 8) tiles
-    int32_t     wait_prior;   // 1: launched programmatically behind K-sdft, wait for it before exiting
-};
-
 // Sliding partial-DFT path of one window group ("K-sdft").  When consecutive frames overlap (hop H much
 // smaller than the window N) and the sparse kernel consumes only a few low bins of the group's FFT,
 // the consumed bins are cheaper as sums of hop-sized partial DFTs that neighbouring frames share:
@@ -85,7 +77,7 @@ struct SdftGroup {
     int32_t hop_pad;        // 16 * n_blocks
     const float2 *tw_a;     // [n_blocks][nk]
     const float2 *tw_b;     // [16][nk]
-    const double2 *phase;   // [q + 1][nk], f64 (the combine runs in f64)
+    const float2 *phase;    // [q + 1][nk]
 };
 
 struct SdftParams {
@@ -99,10 +91,28 @@ struct SdftParams {
     uint32_t     frames;
     uint32_t     rows_per_stream;  // chunk rows per stream: frames + q
     int32_t      spec_stride;
-    double2     *partial_c;        // [n_streams * rows_per_stream][nk], f64 (see sdft_partial_kernel)
-    double2     *partial_r;
+    float2      *partial_c;        // [n_streams * rows_per_stream][nk]
+    float2      *partial_r;
     float       *spec;             // tiled planar layout; local frame = stream_local * frames + t
 };
+
+struct FftParams {
+    FftGroup    group[kMaxGroups];
+    int32_t     n_groups;
+    int32_t     spec_stride;  // columns per tile (multiple of 8)
+    FrameLayout frames;
+    float      *spec;         // tiled planar layout, ceil(n_frames / 8) tiles
+    int32_t     wait_prior;   // 1: launched programmatically behind K-sdft, wait for it before exiting
+    int32_t     n_sdft;       // K-sdft groups whose combine step the CTAs of FFT group `combine_group` run
+    int32_t     combine_group;
+    SdftParams  sdft[kMaxSdft];     // (see sdft_combine.cuh)
+};
+
+// shared memory of the stand-alone combine kernel: the chunk rows of one 8-frame tile
+__host__ __device__ inline size_t sdft_combine_smem_bytes_dev(int q, int nk)
+{
+    return (size_t)(q + kTileFrames) * nk * sizeof(float2);  // + 1 row: alignment slack
+}
 
 constexpr int kSdftThreads = 256;     // 4 row groups x 2 bin halves (64 bins per CTA)
 constexpr int kSdftRowsPerWarp = 4;   // chunk rows a lane accumulates concurrently

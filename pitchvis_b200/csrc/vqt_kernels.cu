@@ -17,6 +17,7 @@
 // X[k] = sum_n x[n] exp(-2 pi i k n / N), half spectrum k = 0..N/2.
 #include "vqt_device.cuh"
 #include "device_helpers.cuh"
+#include "sdft_combine.cuh"
 
 #include <algorithm>
 
@@ -316,6 +317,17 @@ __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant
     // Launched programmatically behind K-sdft (which runs beside this kernel): do not complete before it
     // has, so that the kernels after this one see the partial sums too.
     if (P.wait_prior) pdl_wait();
+    // The CTAs of one FFT group also run the combine step of the K-sdft groups for the frames they own,
+    // reusing the FFT's shared memory.  The host picks the last group: its CTAs are scheduled when the
+    // partial sums are long complete, so the wait below never holds SM slots.
+    if (P.n_sdft > 0 && gi == P.combine_group) {
+        if (!P.wait_prior) pdl_wait();
+        __syncthreads();
+        const uint32_t lf0 = (blockIdx.x - g.cta_begin) * g.frames_per_cta;
+        for (int i = 0; i < P.n_sdft; ++i)
+            sdft_combine_frames(P.sdft[i], lf0, g.frames_per_cta, fft_smem,
+                                sizeof(float2) * (size_t)pad_index(BLOCK * kPointsPerThread));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
