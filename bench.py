@@ -350,6 +350,7 @@ def main():
                     "d2h_bytes_per_step": int(n_frames * nb * 4), "steps": e2e_steps,
                     "api": "pvqt_calc_batch_db (pinned host buffers in and out)", "checksum": result_checksum},
             "gpu_launches": int(launches),
+            "plan": vqt.plan_info(),
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "kernel": _ffi.KERNEL_KIND_NAMES[top], "achieved": achieved, "peak": peak,

@@ -188,13 +188,21 @@ uint64_t pvqt_launch_count(const pvqt *v);
  * launching stream.  pvqt_get_profile synchronises and returns the summed durations and launch
  * counts since the last reset, indexed by kernel kind: 0 = K-fft, 1 = K-spmm (unfused fallback),
  * 2 = K-db (unfused fallback), 3 = K-spmm-db (fused), 4 = K-sdft (sliding partial DFTs),
- * 5 = K-sdft-combine; both arrays hold PVQT_PROFILE_KINDS entries. */
+ * 5 = K-sdft-combine (stand-alone), 6 = K-spmm-db cluster form; both arrays hold PVQT_PROFILE_KINDS entries. */
 #define PVQT_PROFILE_KINDS 8
 int pvqt_set_profiling(pvqt *v, int enabled);
 int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches);
-/* Test / tuning switch: 0 forces the unfused K-spmm + K-db pair, 1 (default) uses K-spmm-db when the
- * kernel fits one CTA.  Returns the value in effect. */
-int pvqt_set_fused_epilogue(pvqt *v, int enabled);
+/* Test / tuning switch for the SpMM + power_to_db stage: 0 = unfused K-spmm + K-db pair, 1 = K-spmm-db with
+ * one CTA per tile (default), 2 = K-spmm-db in its cluster form (coefficients stationary in shared memory,
+ * frame max / min exchanged through distributed shared memory; measured slower at the default parameters,
+ * kept selectable).  A mode the kernel does not fit falls back to the next lower one.  Returns the mode in
+ * effect. */
+int pvqt_set_fused_epilogue(pvqt *v, int mode);
+/* Plan introspection for tests and bench reports; out[0..n) (n <= 8): cluster size of K-spmm-db's cluster form
+ * (0: not available), co-resident clusters, shared-memory bytes of its coefficients, rows of its largest
+ * part, warps of the one-CTA-per-tile form (0: not available), K-fft block size, columns per spectrum tile,
+ * K-sdft plans cached. */
+int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n);
 /* Test / tuning switch: 0 keeps every window group on the per-frame FFT path, 1 (default) lets groups
  * whose consumed bins are cheaper as sums of hop-sized partial DFTs shared between overlapping frames take
  * the K-sdft path in the batched entries (never in the per-frame / independent-frames entries).  Both

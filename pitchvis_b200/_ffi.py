@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libpvqt.so")
 
 PROFILE_KINDS = 8  # PVQT_PROFILE_KINDS
 KERNEL_KIND_NAMES = ("fft_groups_kernel", "spmm_kernel", "power_to_db_kernel", "spmm_db_fused_kernel",
-                     "sdft_partial_kernel", "sdft_combine_kernel", "reserved6", "reserved7")
+                     "sdft_partial_kernel", "sdft_combine_kernel", "spmm_db_cluster_kernel", "reserved7")
 
 (PVQT_OK, PVQT_ABOVE_NYQUIST, PVQT_WINDOW_EXCEEDS_NFFT, PVQT_PANIC, PVQT_BAD_LENGTH, PVQT_INVALID_ARGUMENT,
  PVQT_UNSUPPORTED, PVQT_CUDA_ERROR, PVQT_OUT_OF_MEMORY) = range(9)
@@ -161,6 +161,7 @@ SIGNATURES = {
     "pvqt_get_profile": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pvqt_set_fused_epilogue": (C.c_int, [_VP, C.c_int]),
     "pvqt_set_sliding_dft": (C.c_int, [_VP, C.c_int]),
+    "pvqt_plan_info": (C.c_int, [_VP, C.POINTER(C.c_int32), _SZ]),
     "pvqt_shard_range": (C.c_int, [_SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "pvqt_frame_range_samples": (C.c_int, [_SZ, _SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "pvqt_multi_create": (C.c_int, [C.POINTER(PvqtParams), C.c_int, C.POINTER(C.c_int), C.POINTER(_VP),

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace pvqt_dev {
@@ -37,6 +38,49 @@ __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// SpMM multiply-accumulate and power_to_db pieces shared by the SpMM kernels
+// ------------------------------------------------------------------------------------------
+// One kernel coefficient k applied to the 8 frames of one spectrum record.  Accumulators are planar
+// frame pairs: re[p] = (Re y_f2p, Re y_f2p+1), im[p] likewise; xr* / xi* are the record's chunks.
+//   y += k x:        re += k.re xr - k.im xi,   im += k.re xi + k.im xr          (vqt.rs:889-894)
+//   y += k conj(x):  re += k.re xr + k.im xi,   im += k.im xr - k.re xi          (vqt.rs:896-910)
+template <bool kConj>
+__device__ __forceinline__ void mac8(float2 (&re)[4], float2 (&im)[4], float kre, float kim, const float4 &xr03,
+                                     const float4 &xr47, const float4 &xi03, const float4 &xi47)
+{
+    const float2 xr[4] = {make_float2(xr03.x, xr03.y), make_float2(xr03.z, xr03.w), make_float2(xr47.x, xr47.y),
+                          make_float2(xr47.z, xr47.w)};
+    const float2 xi[4] = {make_float2(xi03.x, xi03.y), make_float2(xi03.z, xi03.w), make_float2(xi47.x, xi47.y),
+                          make_float2(xi47.z, xi47.w)};
+    const float s_im_xi = kConj ? kim : -kim;   // coefficient of xi in re
+    const float s_re_xi = kConj ? -kre : kre;   // coefficient of xi in im
+    const float2 a = make_float2(kre, kre), b = make_float2(s_im_xi, s_im_xi), c = make_float2(s_re_xi, s_re_xi),
+                 d = make_float2(kim, kim);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        re[p] = __ffma2_rn(a, xr[p], re[p]);
+        re[p] = __ffma2_rn(b, xi[p], re[p]);
+        im[p] = __ffma2_rn(c, xi[p], im[p]);
+        im[p] = __ffma2_rn(d, xr[p], im[p]);
+    }
+}
+
+constexpr float kAMin = 1e-6f * 1e-6f;  // vqt.rs:924
+constexpr float kTopDb = 60.0f;         // vqt.rs:925
+
+__device__ __forceinline__ float log_spec(float p, float ref_db)
+{
+    return 10.0f * log10f(fmaxf(p, kAMin)) - ref_db;  // vqt.rs:930
+}
+
+__device__ __forceinline__ float db_out(float l, float floor_db, float log_spec_min)
+{
+    const float clamped = fmaxf(l, floor_db);          // vqt.rs:945-950
+    return log_spec_min > 0.0f ? clamped - log_spec_min : fmaxf(clamped, 0.0f);
 }
 
 

@@ -126,6 +126,9 @@ struct pvqt {
     FusedParams fused{};                // K-spmm-db plan (one CTA per tile owns every row)
     bool fused_capable = false;         // false: the kernel is too large for one CTA -> K-spmm + K-db
     bool fused_ok = false;              // fused_capable and not switched off (pvqt_set_fused_epilogue)
+    ClusterParams cluster{};            // K-spmm-db, cluster form (coefficients stationary in shared memory)
+    bool cluster_capable = false, cluster_ok = false;
+    int cluster_max_active = 0;         // co-resident clusters (cudaOccupancyMaxActiveClusters)
     int fft_block_threads = 256;
     float ref_db = 0.0f;
     std::vector<uint32_t> col_lo, n_cols, spec_off;
@@ -175,6 +178,7 @@ cudaError_t upload(pvqt *v, const std::vector<T> &host, const T **dev)
 }
 
 int build_fused_plan(pvqt *v);
+int build_cluster_plan(pvqt *v);
 
 int build_device_plan(pvqt *v)
 {
@@ -356,7 +360,9 @@ int build_device_plan(pvqt *v)
 
     if ((e = configure_kernels(max_cols)) != cudaSuccess)
         return cuda_fail(e, "configure kernels (is this an sm_100a device?)");
-    return build_fused_plan(v);
+    int rc = build_fused_plan(v);
+    if (rc != PVQT_OK) return rc;
+    return build_cluster_plan(v);
 }
 
 // ---- K-spmm-db plan: row pairs sorted by band length, dealt to warps, bank-conflict-free lanes ----
@@ -483,7 +489,7 @@ int build_fused_plan(pvqt *v)
             }
         }
     }
-    values.resize(values.size() + (size_t)2 * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
+    values.resize(values.size() + (size_t)2 * kFusedRing * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
 
     FusedParams &P = v->fused;
     std::memset(&P, 0, sizeof(P));
@@ -567,6 +573,236 @@ const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
     return &v->sdft_plans.back();
 }
 
+// ---- K-spmm-db cluster plan: CS contiguous row parts, 8 row pairs per warp, bands split in two halves ----
+int build_cluster_plan(pvqt *v)
+{
+    const auto &groups = v->kernel.window_groups;
+    const FftParams &F = v->fft;
+    struct Unit {
+        int col0 = 0, len = 0, ncol0 = 0, nlen = 0;
+        int first_row = 0, n_rows = 0, group = 0, local_row = 0;
+    };
+    std::vector<Unit> units;
+    int first_row = 0;
+    long total_work = 0;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        const auto &g = groups[gi];
+        const int spec = F.group[gi].spec_offset, lo = F.group[gi].col_lo;
+        for (int r0 = 0; r0 < g.filter_bank.rows; r0 += kRowsPerLane) {
+            Unit u;
+            u.group = (int)gi; u.local_row = r0; u.first_row = first_row + r0;
+            u.n_rows = std::min(kRowsPerLane, g.filter_bank.rows - r0);
+            int a0 = 1 << 30, a1 = -1, n0 = 1 << 30, n1 = -1;
+            for (int q = 0; q < u.n_rows; ++q) {
+                const int r = r0 + q;
+                const int s = g.filter_bank.indptr[r], e = g.filter_bank.indptr[r + 1];
+                if (e > s) {
+                    a0 = std::min(a0, spec + g.filter_bank.indices[s] - lo);
+                    a1 = std::max(a1, spec + g.filter_bank.indices[e - 1] - lo + 1);
+                }
+                if (g.negative_filter_bank.nnz() > 0) {
+                    const int ns = g.negative_filter_bank.indptr[r], ne = g.negative_filter_bank.indptr[r + 1];
+                    if (ne > ns) {
+                        n0 = std::min(n0, spec + g.negative_filter_bank.indices[ns] - lo);
+                        n1 = std::max(n1, spec + g.negative_filter_bank.indices[ne - 1] - lo + 1);
+                    }
+                }
+            }
+            if (a1 >= 0) { u.col0 = a0; u.len = a1 - a0; }
+            if (n1 >= 0) { u.ncol0 = n0; u.nlen = n1 - n0; }
+            total_work += u.len + u.nlen + 4;
+            units.push_back(u);
+        }
+        first_row += g.filter_bank.rows;
+    }
+    if (units.empty()) return PVQT_OK;
+
+    struct WarpPlan { int width = 0, nwidth = 0, slot_base = 0, nslot_base = 0; std::vector<Unit> u; };
+    struct PartPlan { std::vector<WarpPlan> warps; int col_lo = 0, cols_needed = 0, n_cols = 0, row_lo = 0, n_rows = 0, slots = 0; };
+    const int max_warps = kClusterThreads / 32;
+    std::vector<PartPlan> parts;
+    int cs = 0;
+    for (int cand : {1, 2, 4, 8}) {
+        parts.assign((size_t)cand, PartPlan());
+        // contiguous split of the row-ordered units, balanced on the band slots the parts will walk (a part's
+        // cost is the sum over its 8-unit warps of half the warp's longest band, estimated by plan_slots)
+        auto plan_slots = [&](size_t b, size_t e) {
+            std::vector<int> lens, nlens;
+            for (size_t i = b; i < e; ++i) { lens.push_back(units[i].len); nlens.push_back(units[i].nlen); }
+            std::sort(lens.begin(), lens.end(), std::greater<int>());
+            std::sort(nlens.begin(), nlens.end(), std::greater<int>());
+            long sl = 0;
+            for (size_t i = 0; i < lens.size(); i += 8) sl += (lens[i] + 4) / 2 + nlens[i];
+            return sl;
+        };
+        std::vector<size_t> bound((size_t)cand + 1);
+        for (int p = 0; p <= cand; ++p) bound[(size_t)p] = units.size() * (size_t)p / (size_t)cand;
+        for (int iter = 0; iter < 200 && cand > 1; ++iter) {
+            int worst = 0;
+            long worst_slots = -1;
+            for (int p = 0; p < cand; ++p) {
+                const long sl = plan_slots(bound[(size_t)p], bound[(size_t)p + 1]);
+                if (sl > worst_slots) { worst_slots = sl; worst = p; }
+            }
+            // give one unit of the heaviest part to its lighter neighbour
+            const long left = worst > 0 ? plan_slots(bound[(size_t)worst - 1], bound[(size_t)worst]) : (1L << 60);
+            const long right = worst + 1 < cand ? plan_slots(bound[(size_t)worst + 1], bound[(size_t)worst + 2]) : (1L << 60);
+            if (std::min(left, right) + 2 >= worst_slots) break;
+            if (bound[(size_t)worst + 1] - bound[(size_t)worst] <= 1) break;
+            if (left <= right) ++bound[(size_t)worst]; else --bound[(size_t)worst + 1];
+        }
+        // a part's staged column range must fit the compile-time plane width: shrink offenders
+        auto col_span = [&](size_t b, size_t e) {
+            int lo = 1 << 30, hi = 0;
+            for (size_t i = b; i < e; ++i) {
+                const Unit &u = units[i];
+                if (u.len > 0) { lo = std::min(lo, u.col0 - 7); hi = std::max(hi, u.col0 + ((u.len + 8) / 2) * 2 + 2); }
+                if (u.nlen > 0) { lo = std::min(lo, u.ncol0); hi = std::max(hi, u.ncol0 + u.nlen); }
+            }
+            return hi > 0 ? hi - (std::max(lo, 0) & ~7) : 0;
+        };
+        for (int iter = 0; iter < 400 && cand > 1; ++iter) {
+            int bad = -1;
+            for (int p = 0; p < cand; ++p)
+                if (col_span(bound[(size_t)p], bound[(size_t)p + 1]) > kClusterPlaneCols) { bad = p; break; }
+            if (bad < 0) break;
+            if (bound[(size_t)bad + 1] - bound[(size_t)bad] <= 1) break;
+            if (bad == cand - 1) ++bound[(size_t)bad]; else --bound[(size_t)bad + 1];
+        }
+        std::vector<std::vector<Unit>> pu((size_t)cand);
+        for (int p = 0; p < cand; ++p)
+            pu[(size_t)p].assign(units.begin() + (long)bound[(size_t)p], units.begin() + (long)bound[(size_t)p + 1]);
+        bool ok = true;
+        int coef_slots_max = 0, rows_max = 0;
+        for (int p = 0; p < cand && ok; ++p) {
+            PartPlan &pp = parts[(size_t)p];
+            std::vector<Unit> us = pu[(size_t)p];
+            if (us.empty()) { ok = false; break; }
+            pp.row_lo = us.front().first_row;
+            for (const Unit &u : us) pp.n_rows += u.n_rows;
+            std::stable_sort(us.begin(), us.end(), [](const Unit &a, const Unit &b) { return a.len > b.len; });
+            const int nw = (int)((us.size() + 7) / 8);
+            if (nw > max_warps) { ok = false; break; }
+            int cmin = 1 << 30, cmax = 0, slots = 0;
+            for (int w = 0; w < nw; ++w) {
+                WarpPlan wp;
+                const size_t u0 = (size_t)w * 8, u1 = std::min(us.size(), u0 + 8);
+                // distinct start residues modulo 8 inside the warp (or the same column): each quarter-warp
+                // LDS.128 of the band walk is then conflict-free.  A unit may start up to 7 columns early.
+                int residue_col[8];
+                for (int &c : residue_col) c = -1;
+                for (size_t i = u0; i < u1; ++i) {
+                    Unit u = us[i];
+                    if (u.len > 0) {
+                        int shift = 0;
+                        for (; shift < 8; ++shift) {
+                            const int c = u.col0 - shift;
+                            if (c < 0) { shift = 8; break; }
+                            if (residue_col[c & 7] == -1 || residue_col[c & 7] == c) break;
+                        }
+                        if (shift < 8) { u.col0 -= shift; u.len += shift; }
+                        if (residue_col[u.col0 & 7] == -1) residue_col[u.col0 & 7] = u.col0;
+                    }
+                    wp.u.push_back(u);
+                    wp.width = std::max(wp.width, (u.len + 1) / 2);
+                    wp.nwidth = std::max(wp.nwidth, u.nlen);
+                }
+                for (const Unit &u : wp.u) {
+                    if (u.len > 0) { cmin = std::min(cmin, u.col0); cmax = std::max(cmax, u.col0 + 2 * wp.width); }
+                    if (u.nlen > 0) { cmin = std::min(cmin, u.ncol0); cmax = std::max(cmax, u.ncol0 + wp.nwidth); }
+                }
+                wp.slot_base = slots; slots += wp.width;
+                wp.nslot_base = slots; slots += wp.nwidth;
+                pp.warps.push_back(std::move(wp));
+            }
+            if (cmax <= 0) { cmin = 0; cmax = 8; }
+            pp.col_lo = cmin & ~7;
+            pp.cols_needed = cmax - pp.col_lo;
+            pp.n_cols = std::min(pp.cols_needed, F.spec_stride - pp.col_lo);
+            pp.slots = slots;
+            if (pp.cols_needed > kClusterPlaneCols) ok = false;
+            coef_slots_max = std::max(coef_slots_max, slots);
+            rows_max = std::max(rows_max, pp.n_rows);
+        }
+        if (!ok) continue;
+        const int coef_bytes = (coef_slots_max * 256 + 127) & ~127;
+        if (cluster_smem_bytes(coef_bytes, rows_max, cand) > 227 * 1024) continue;
+        cs = cand;
+        v->cluster.coef_bytes = coef_bytes;
+        v->cluster.max_rows = rows_max;
+        v->cluster.mm_offset = (int32_t)(cluster_smem_bytes(coef_bytes, rows_max, cand) -
+                                         (size_t)2 * cand * kClusterRoundFrames * sizeof(float2));
+        break;
+    }
+    if (cs == 0) return PVQT_OK;  // does not fit: the single-CTA or unfused kernels take over
+
+    std::vector<ClusterPart> dparts;
+    std::vector<ClusterWarp> dwarps;
+    std::vector<ClusterLane> dlanes;
+    std::vector<float4> coef;
+    for (const PartPlan &pp : parts) {
+        ClusterPart dp{};
+        dp.n_warps = (int)pp.warps.size();
+        dp.col_lo = pp.col_lo; dp.n_cols = pp.n_cols; dp.cols_touched = pp.cols_needed;
+        dp.row_lo = pp.row_lo; dp.n_rows = pp.n_rows;
+        dp.coef_base = (int)(coef.size() / 16); dp.coef_slots = pp.slots; dp.desc_base = (int)dwarps.size();
+        coef.resize(coef.size() + (size_t)pp.slots * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (const WarpPlan &wp : pp.warps) {
+            dwarps.push_back(ClusterWarp{wp.width, wp.nwidth, wp.slot_base, wp.nslot_base});
+            const size_t lane0 = dlanes.size();
+            dlanes.resize(lane0 + 16, ClusterLane{0, 0, -1, 0});
+            for (size_t ui = 0; ui < wp.u.size(); ++ui) {
+                const Unit &u = wp.u[ui];
+                const auto &g = groups[(size_t)u.group];
+                const int spec = F.group[u.group].spec_offset, lo = F.group[u.group].col_lo;
+                for (int h = 0; h < 2; ++h) {
+                    ClusterLane &L = dlanes[lane0 + (size_t)h * 8 + ui];
+                    L.col = (u.len > 0 ? u.col0 - pp.col_lo : 0) + h * wp.width;
+                    L.ncol = u.nlen > 0 ? u.ncol0 - pp.col_lo : 0;
+                    L.row = u.first_row - pp.row_lo;
+                    L.n_rows = u.n_rows;
+                }
+                for (int q = 0; q < u.n_rows; ++q) {
+                    const int r = u.local_row + q;
+                    for (int e = g.filter_bank.indptr[r]; e < g.filter_bank.indptr[r + 1]; ++e) {
+                        const int pos = spec + g.filter_bank.indices[e] - lo - u.col0;
+                        const int h = pos / wp.width, j = pos % wp.width;
+                        float4 &slot = coef[((size_t)dp.coef_base + wp.slot_base + j) * 16 + (size_t)h * 8 + ui];
+                        (q == 0 ? slot.x : slot.z) = g.filter_bank.data[e].real();
+                        (q == 0 ? slot.y : slot.w) = g.filter_bank.data[e].imag();
+                    }
+                    if (u.nlen > 0)
+                        for (int e = g.negative_filter_bank.indptr[r]; e < g.negative_filter_bank.indptr[r + 1]; ++e) {
+                            const int j = spec + g.negative_filter_bank.indices[e] - lo - u.ncol0;
+                            float4 &slot = coef[((size_t)dp.coef_base + wp.nslot_base + j) * 16 + ui];
+                            // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg); the h = 1 lanes keep zeros
+                            (q == 0 ? slot.x : slot.z) = g.negative_filter_bank.data[e].real();
+                            (q == 0 ? slot.y : slot.w) = -g.negative_filter_bank.data[e].imag();
+                        }
+                }
+            }
+        }
+        dparts.push_back(dp);
+    }
+
+    ClusterParams &P = v->cluster;
+    cudaError_t e;
+    if ((e = upload(v, dparts, &P.parts)) != cudaSuccess || (e = upload(v, dwarps, &P.warps)) != cudaSuccess ||
+        (e = upload(v, dlanes, &P.lanes)) != cudaSuccess || (e = upload(v, coef, &P.coef)) != cudaSuccess)
+        return cuda_fail(e, "upload cluster plan");
+    P.cluster_size = cs;
+    P.n_buckets = (int32_t)v->kernel.n_buckets;
+    P.spec_stride = F.spec_stride;
+    P.ref_db = v->ref_db;
+    int max_active = 0;
+    e = configure_cluster(P.coef_bytes, P.max_rows, cs, &max_active);
+    if (e != cudaSuccess || max_active <= 0) { cudaGetLastError(); return PVQT_OK; }  // keep the other kernels
+    v->cluster_max_active = max_active;
+    v->cluster_capable = true;
+    v->cluster_ok = false;  // measured slower than the one-CTA-per-tile form on B200: opt-in, mode 2
+    return PVQT_OK;
+}
+
 void prof_begin(pvqt *v, int kind, cudaStream_t stream)
 {
     if (!v->profiling) return;
@@ -618,7 +854,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     const size_t chunk = v->chunk_frames;  // multiple of kTileFrames
     const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
     if (!d_spec_out) {
-        int rc = reserve_scratch(v, std::min(total, chunk), d_power == nullptr && !v->fused_ok, stream);
+        int rc = reserve_scratch(v, std::min(total, chunk), d_power == nullptr && !v->fused_ok && !v->cluster_ok, stream);
         if (rc) return rc;
     }
 
@@ -728,6 +964,21 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             if (d_spec_out) continue;
 
             cudaError_t e;
+            if (v->cluster_ok) {
+                ClusterParams cp = v->cluster;
+                cp.n_frames = n;
+                cp.n_tiles = (n + kTileFrames - 1) / kTileFrames;
+                cp.spec = spec;
+                cp.out_db = d_out + f0 * nb;
+                cp.power = d_power ? d_power + f0 * nb : nullptr;
+                const int rounds = (int)((cp.n_tiles + 1) / 2);
+                prof_begin(v, 6, stream);
+                e = launch_spmm_db_cluster(cp, std::min(rounds, v->cluster_max_active), stream);
+                if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_cluster_kernel");
+                prof_end(v, stream);
+                v->launches.fetch_add(1);
+                continue;
+            }
             if (v->fused_ok) {
                 FusedParams up = v->fused;
                 up.n_frames = n;
@@ -916,7 +1167,7 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         const size_t frames = n_streams * frames_per_stream;
         PVQT_CUDA(v->d_audio.reserve(audio_samples * sizeof(float)));
         PVQT_CUDA(v->d_out.reserve(frames * J.nb * sizeof(float)));
-        int rc = reserve_scratch(v, frames, !v->fused_ok, v->stream);
+        int rc = reserve_scratch(v, frames, !v->fused_ok && !v->cluster_ok, v->stream);
         if (rc) return rc;
         auto enqueue = [&]() -> int {
             int r = fork_streams(v, ev);
@@ -1374,12 +1625,23 @@ int pvqt_set_profiling(pvqt *v, int enabled)
     return PVQT_OK;
 }
 
-int pvqt_set_fused_epilogue(pvqt *v, int enabled)
+int pvqt_set_fused_epilogue(pvqt *v, int mode)
 {
     if (!v) return 0;
-    v->fused_ok = v->fused_capable && enabled != 0;
+    v->cluster_ok = v->cluster_capable && mode >= 2;
+    v->fused_ok = v->fused_capable && mode >= 1;
     if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
-    return v->fused_ok ? 1 : 0;
+    return v->cluster_ok ? 2 : (v->fused_ok ? 1 : 0);
+}
+
+int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
+{
+    if (!v || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    const int32_t info[8] = {v->cluster_capable ? v->cluster.cluster_size : 0, v->cluster_max_active, v->cluster.coef_bytes,
+                             v->cluster.max_rows, v->fused_capable ? v->fused.n_warps : 0, v->fft_block_threads,
+                             v->fft.spec_stride, (int32_t)v->sdft_plans.size()};
+    for (size_t i = 0; i < n && i < 8; ++i) out[i] = info[i];
+    return PVQT_OK;
 }
 
 int pvqt_set_sliding_dft(pvqt *v, int enabled)

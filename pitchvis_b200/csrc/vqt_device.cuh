@@ -184,6 +184,62 @@ struct FusedParams {
     float    ref_db;
 };
 
+// K-spmm-db, cluster form ("coefficient-stationary"): a thread-block cluster of CS CTAs splits the kernel
+// rows into CS contiguous parts; each CTA keeps its part's coefficients in shared memory for the whole
+// launch and streams 16-frame rounds (two tiles) through; the frame-wise max / min of power_to_db are
+// exchanged between the CTAs of the cluster through distributed shared memory.
+struct ClusterPart {
+    int32_t n_warps;     // warps of this part that own band slots
+    int32_t col_lo;      // first spectrum column staged (multiple of 8)
+    int32_t n_cols;      // columns staged per tile (clipped to the tile's spec_stride)
+    int32_t cols_touched; // columns the band halves may read (>= n_cols; the excess is zero-filled)
+    int32_t row_lo;      // first output row owned
+    int32_t n_rows;      // rows owned (contiguous)
+    int32_t coef_base;   // first coefficient slot of the part in `coef` (slot = 16 float4)
+    int32_t coef_slots;  // slots of the part
+    int32_t desc_base;   // first warp descriptor / 16-lane group of the part
+};
+struct ClusterWarp {
+    int32_t width;       // band slots per lane: half the longest band of the warp's 8 row pairs
+    int32_t nwidth;      // conjugate-part slots
+    int32_t slot_base;   // first slot of the warp, relative to the part's coef_base
+    int32_t nslot_base;
+};
+struct ClusterLane {     // per (warp, half h, unit u): 16 per warp
+    int32_t col;         // first column of this lane's half band, relative to col_lo
+    int32_t ncol;        // first column of the conjugate-part band
+    int32_t row;         // first output row relative to row_lo (-1: none)
+    int32_t n_rows;      // 0..2
+};
+struct ClusterParams {
+    const ClusterPart *parts;
+    const ClusterWarp *warps;
+    const ClusterLane *lanes;
+    const float4 *coef;
+    int32_t  cluster_size;
+    int32_t  n_buckets;
+    int32_t  spec_stride;
+    int32_t  max_rows;      // largest n_rows over parts (the log-spectrum buffer aliases the staged tiles)
+    int32_t  coef_bytes;    // shared memory reserved for the coefficients (largest part)
+    int32_t  mm_offset;     // byte offset of the max / min exchange slots (after the tiles / log-spectrum buffer)
+    uint32_t n_frames;
+    uint32_t n_tiles;
+    const float *spec;
+    float   *out_db;
+    float   *power;
+    float    ref_db;
+};
+constexpr int kClusterPlaneCols = 384;   // columns per chunk plane of a staged tile (compile-time: immediates)
+constexpr int kClusterThreads = 384;     // 12 warps: up to 96 row pairs per part; two CTAs share an SM
+constexpr int kClusterRoundFrames = 2 * kTileFrames;
+
+constexpr int kFusedRing = 4;   // coefficient slots the one-CTA-per-tile K-spmm-db keeps in flight per lane
+// float4 entries of its staging / log-spectrum region: max(n_cols records of 64 bytes, ls[8][n_buckets])
+__host__ __device__ inline int fused_stage_f4(int n_cols, int n_buckets)
+{
+    const int stage = n_cols * 4, ls = (kTileFrames * n_buckets + 3) / 4;
+    return stage > ls ? stage : ls;
+}
 constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
 constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
 
@@ -198,8 +254,11 @@ size_t sdft_smem_bytes(int hop_pad);
 cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream);
 cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream);
 cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream);
+size_t      cluster_smem_bytes(int coef_bytes, int max_rows, int cluster_size);
+cudaError_t configure_cluster(int coef_bytes, int max_rows, int cluster_size, int *max_clusters);
+cudaError_t launch_spmm_db_cluster(const ClusterParams &p, int n_clusters, cudaStream_t stream);
 bool        fused_supported(int n_warps, int n_cols, int n_buckets);
-size_t      fused_smem_bytes(int n_cols, int n_buckets);
+size_t      fused_smem_bytes(int n_cols, int n_buckets, int n_warps);
 cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets);
 cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);

@@ -333,31 +333,6 @@ __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant
 // ------------------------------------------------------------------------------------------
 // K-spmm: banded complex SpMM, kernel-stationary
 // ------------------------------------------------------------------------------------------
-// One kernel coefficient k applied to the 8 frames of one spectrum record.  Accumulators are planar
-// frame pairs: re[p] = (Re y_f2p, Re y_f2p+1), im[p] likewise; xr* / xi* are the record's chunks.
-//   y += k x:        re += k.re xr - k.im xi,   im += k.re xi + k.im xr          (vqt.rs:889-894)
-//   y += k conj(x):  re += k.re xr + k.im xi,   im += k.im xr - k.re xi          (vqt.rs:896-910)
-template <bool kConj>
-__device__ __forceinline__ void mac8(float2 (&re)[4], float2 (&im)[4], float kre, float kim, const float4 &xr03,
-                                     const float4 &xr47, const float4 &xi03, const float4 &xi47)
-{
-    const float2 xr[4] = {make_float2(xr03.x, xr03.y), make_float2(xr03.z, xr03.w), make_float2(xr47.x, xr47.y),
-                          make_float2(xr47.z, xr47.w)};
-    const float2 xi[4] = {make_float2(xi03.x, xi03.y), make_float2(xi03.z, xi03.w), make_float2(xi47.x, xi47.y),
-                          make_float2(xi47.z, xi47.w)};
-    const float s_im_xi = kConj ? kim : -kim;   // coefficient of xi in re
-    const float s_re_xi = kConj ? -kre : kre;   // coefficient of xi in im
-    const float2 a = make_float2(kre, kre), b = make_float2(s_im_xi, s_im_xi), c = make_float2(s_re_xi, s_re_xi),
-                 d = make_float2(kim, kim);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        re[p] = __ffma2_rn(a, xr[p], re[p]);
-        re[p] = __ffma2_rn(b, xi[p], re[p]);
-        im[p] = __ffma2_rn(c, xi[p], im[p]);
-        im[p] = __ffma2_rn(d, xr[p], im[p]);
-    }
-}
-
 // Grid: (row block, group of kSpmmWarps tiles), widest row blocks first.  Each warp owns one 8-frame
 // tile: it stages the columns its block reads (contiguous 64-byte records of the tiled spectrum) with
 // cp.async, then walks the block's band; lane l accumulates rows first_row + 2l and + 2l + 1 for the
@@ -461,20 +436,6 @@ __global__ void __launch_bounds__(kSpmmWarps * 32) spmm_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------
 constexpr int kDbWarps = 8;
 constexpr int kDbMaxPerLane = 8;        // register-resident path: n_buckets <= 32 * 4 * 8 = 1024
-constexpr float kAMin = 1e-6f * 1e-6f;  // vqt.rs:924
-constexpr float kTopDb = 60.0f;         // vqt.rs:925
-
-__device__ __forceinline__ float log_spec(float p, float ref_db)
-{
-    return 10.0f * log10f(fmaxf(p, kAMin)) - ref_db;  // vqt.rs:930
-}
-
-__device__ __forceinline__ float db_out(float l, float floor_db, float log_spec_min)
-{
-    const float clamped = fmaxf(l, floor_db);          // vqt.rs:945-950
-    return log_spec_min > 0.0f ? clamped - log_spec_min : fmaxf(clamped, 0.0f);
-}
-
 // kVec: n_buckets % 4 == 0 and <= 1024 -> every lane keeps its float4s in registers (one pass over memory)
 template <bool kVec>
 __global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid_constant__ DbParams P)
@@ -552,7 +513,16 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     const int2 rows = __ldg(P.lane_rows + warp * 32 + lane);
     const float4 *kv = P.values + (size_t)W.val_base * 32 + lane;
     const float4 *nv = P.values + (size_t)W.nval_base * 32 + lane;
-    float4 kq = __ldg(kv);  // `values` ends with spare slots: the prefetch below may overrun by one
+    // The coefficient stream goes through a lane-private ring in shared memory filled with cp.async
+    // kFusedRing slots ahead: a register prefetch deep enough to cover the L2 latency does not fit the
+    // 64-register budget of three resident CTAs (profiles/r01_d: the wait on that load was 26 % of all stall
+    // samples).  Lane l copies and reads only its own 16 bytes of a slot, so no warp-level sync is needed.
+    float4 *ring = fused_smem + fused_stage_f4(P.n_cols, P.n_buckets) + (size_t)warp * kFusedRing * 32 + lane;
+#pragma unroll
+    for (int s = 0; s < kFusedRing; ++s) {  // `values` ends with kFusedRing spare slots
+        cp_async16(ring + s * 32, kv + s * 32);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
 
     pdl_launch_dependents();
     pdl_wait();  // everything above is plan data; the spectra below come from K-fft / K-sdft
@@ -571,8 +541,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
 
 #pragma unroll 1
     for (int j = 0; j < W.width; ++j) {
-        const float4 k = kq;
-        kq = __ldg(kv + (j + 1) * 32);
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kFusedRing - 1));  // slot j has landed
+        float4 *slot = ring + (j & (kFusedRing - 1)) * 32;
+        const float4 k = *slot;
+        cp_async16(slot, kv + (j + kFusedRing) * 32);
+        asm volatile("cp.async.commit_group;\n" ::);
         const int c = meta.x + j;
         const float4 *rec = fused_smem + c * 4;
         const int sw = (c >> 1) & 3;
@@ -738,16 +711,14 @@ cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream)
 }
 
 // ---- K-spmm-db launch -------------------------------------------------------------------------
-size_t fused_smem_bytes(int n_cols, int n_buckets)
+size_t fused_smem_bytes(int n_cols, int n_buckets, int n_warps)
 {
-    const size_t stage = (size_t)n_cols * kTileFrames * sizeof(float2);
-    const size_t ls = (size_t)kTileFrames * n_buckets * sizeof(float);
-    return (std::max(stage, ls) + 15) & ~(size_t)15;
+    return (size_t)fused_stage_f4(n_cols, n_buckets) * sizeof(float4) + (size_t)n_warps * kFusedRing * 32 * sizeof(float4);
 }
 
 bool fused_supported(int n_warps, int n_cols, int n_buckets)
 {
-    return n_warps >= 1 && n_warps <= 32 && fused_smem_bytes(n_cols, n_buckets) <= 200 * 1024;
+    return n_warps >= 1 && n_warps <= 32 && fused_smem_bytes(n_cols, n_buckets, n_warps) <= 200 * 1024;
 }
 
 namespace {
@@ -763,7 +734,7 @@ cudaError_t with_fused_kernel(int n_warps, Fn fn)
 
 cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets)
 {
-    const int smem = (int)fused_smem_bytes(n_cols, n_buckets);
+    const int smem = (int)fused_smem_bytes(n_cols, n_buckets, n_warps);
     return with_fused_kernel(n_warps, [&](auto kernel) {
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
@@ -771,7 +742,7 @@ cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets)
 
 cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream)
 {
-    const size_t smem = fused_smem_bytes(p.n_cols, p.n_buckets);
+    const size_t smem = fused_smem_bytes(p.n_cols, p.n_buckets, p.n_warps);
     return with_fused_kernel(p.n_warps, [&](auto kernel) {
         return launch_dependent(kernel, p.n_tiles, (unsigned)p.n_warps * 32, smem, stream, p);
     });

@@ -232,9 +232,17 @@ class Vqt:
     def launch_count(self) -> int:
         return int(self._lib.pvqt_launch_count(self._h))
 
-    def set_fused_epilogue(self, enabled: bool) -> bool:
-        """Tuning / test switch: False forces the unfused K-spmm + K-db pair.  Returns the value in effect."""
-        return bool(self._lib.pvqt_set_fused_epilogue(self._h, 1 if enabled else 0))
+    def set_fused_epilogue(self, mode: int) -> int:
+        """Tuning / test switch: 0 = unfused K-spmm + K-db, 1 = K-spmm-db one CTA per tile, 2 = cluster form
+        (default).  Returns the mode in effect (a mode the kernel does not fit falls back to a lower one)."""
+        return int(self._lib.pvqt_set_fused_epilogue(self._h, int(mode)))
+
+    def plan_info(self) -> dict:
+        out = (C.c_int32 * 8)()
+        _check(self._lib.pvqt_plan_info(self._h, out, 8))
+        keys = ("cluster_size", "clusters_resident", "cluster_coef_bytes", "cluster_max_rows", "fused_warps",
+                "fft_block_threads", "spec_stride", "sdft_plans")
+        return dict(zip(keys, [int(x) for x in out]))
 
     def set_sliding_dft(self, enabled: bool) -> bool:
         """Tuning / test switch: False keeps every window group on the per-frame FFT path in batched calls."""

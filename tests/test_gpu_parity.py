@@ -160,26 +160,33 @@ def test_power_parity_above_minus_80_db(vqt, oracle_default, chords):
     assert np.abs(db_gpu - db_from_pow).max() <= 2e-5
 
 
-def test_fused_epilogue_matches_unfused_pair(vqt, chords):
-    # K-spmm-db (one CTA per tile owns all rows, dB fused) against K-spmm + K-db: same sums, same order
-    n_frames = 77  # not a multiple of the 8-frame tile
+def test_spmm_db_variants_agree(vqt, oracle_default, chords):
+    """The three forms of the SpMM + power_to_db stage on the same spectra: unfused K-spmm + K-db (0), K-spmm-db
+    one CTA per tile (1: same sums in the same order as 0 -> bit-identical), cluster form (2: band halves are
+    added at the end -> equal within f32 rounding, and within the parity tolerance of the oracle)."""
+    n_frames = 77  # not a multiple of the 8-frame tile nor of the 16-frame round
     audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
     d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
     d_audio.upload(audio)
     res = {}
     try:
-        for fused in (True, False):
-            assert vqt.set_fused_epilogue(fused) == fused
+        for mode in (2, 1, 0):
+            assert vqt.set_fused_epilogue(mode) == mode
             d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
             d_pow = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
             pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, d_pow)
-            res[fused] = (d_out.download((n_frames, 588)), d_pow.download((n_frames, 588)))
+            res[mode] = (d_out.download((n_frames, 588)), d_pow.download((n_frames, 588)))
             pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, None)  # without the optional power output
-            np.testing.assert_array_equal(d_out.download((n_frames, 588)), res[fused][0])
+            np.testing.assert_array_equal(d_out.download((n_frames, 588)), res[mode][0])
     finally:
-        vqt.set_fused_epilogue(True)
-    np.testing.assert_array_equal(res[True][1], res[False][1])
-    np.testing.assert_array_equal(res[True][0], res[False][0])
+        vqt.set_fused_epilogue(1)
+    np.testing.assert_array_equal(res[1][1], res[0][1])
+    np.testing.assert_array_equal(res[1][0], res[0][0])
+    assert _power_err_db(res[2][1], res[0][1], -60.0) <= 5e-4
+    assert np.abs(res[2][0] - res[0][0]).max() <= 5e-4
+    ref = oracle_default.calculate_batch_db(audio, HOP, mode=0)
+    for mode in (0, 1, 2):
+        assert np.abs(res[mode][0] - ref).max() <= TOL_DB, mode
 
 
 def test_frames_streams_and_instant_are_bit_identical(vqt, chords):
