@@ -146,7 +146,17 @@ struct pvqt {
     bool sdft_enabled = true;              // pvqt_set_sliding_dft
 
     // scratch
-    DeviceBuffer spec, power, d_audio, d_out, sdft_c, sdft_r;
+    // One scratch set per launch lane: consecutive launch chains of a call alternate between kLanes internal
+    // streams, so the tail of one chain (few CTAs left) overlaps the head of the next.
+    static constexpr int kLanes = 3;
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DeviceBuffer spec, power, sdft_c, sdft_r;
+    } lane[kLanes];
+    cudaEvent_t lane_fork = nullptr;
+    int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames
+    DeviceBuffer d_audio, d_out;
     std::atomic<uint64_t> launches{0};
 
     // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
@@ -368,6 +378,12 @@ int build_device_plan(pvqt *v)
 // ---- K-spmm-db plan: row pairs sorted by band length, dealt to warps, bank-conflict-free lanes ----
 int build_fused_plan(pvqt *v)
 {
+    // rows per lane: 4 shares every spectrum load between four kernel rows (half the shared-memory traffic per
+    // FMA of 2; the band walk is co-limited by the LDS and FMA pipes, profiles/r01_f); PVQT_ROWS_PER_LANE=2 keeps
+    // the two-row form for comparison.
+    int R = 2;
+    if (const char *e = std::getenv("PVQT_ROWS_PER_LANE")) R = std::atoi(e) == 4 ? 4 : 2;
+    const int H = R / 2;
     const auto &groups = v->kernel.window_groups;
     const FftParams &F = v->fft;
     struct Unit {
@@ -381,10 +397,10 @@ int build_fused_plan(pvqt *v)
         const auto &g = groups[gi];
         const int spec = F.group[gi].spec_offset, lo = F.group[gi].col_lo;
         n_cols = std::max(n_cols, spec + F.group[gi].col_hi - lo + 1);
-        for (int r0 = 0; r0 < g.filter_bank.rows; r0 += kRowsPerLane) {
+        for (int r0 = 0; r0 < g.filter_bank.rows; r0 += R) {
             Unit u;
             u.group = (int)gi; u.local_row = r0; u.first_row = first_row + r0;
-            u.n_rows = std::min(kRowsPerLane, g.filter_bank.rows - r0);
+            u.n_rows = std::min(R, g.filter_bank.rows - r0);
             int a0 = 1 << 30, a1 = -1, n0 = 1 << 30, n1 = -1;
             for (int q = 0; q < u.n_rows; ++q) {
                 const int r = r0 + q;
@@ -410,7 +426,12 @@ int build_fused_plan(pvqt *v)
     std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.len + a.nlen > b.len + b.nlen; });
     const int n_warps = (int)((units.size() + 31) / 32);
     n_cols = std::min<int>((n_cols + 7) & ~7, F.spec_stride);
-    v->fused_capable = v->fused_ok = fused_supported(n_warps, n_cols, (int)v->kernel.n_buckets);
+    // columns the unpredicated band walk may read: start column + the warp's (padded) width; bounded by
+    // n_cols + the longest band + the 7-column placement shift
+    int longest = 0;
+    for (const Unit &u : units) longest = std::max(longest, std::max(u.len, u.nlen));
+    const int touched_bound = n_cols + longest + 8;
+    v->fused_capable = v->fused_ok = fused_supported(n_warps, touched_bound, (int)v->kernel.n_buckets, R);
     if (!v->fused_ok) return PVQT_OK;
 
     std::vector<FusedWarp> warps((size_t)n_warps);
@@ -455,14 +476,13 @@ int build_fused_plan(pvqt *v)
         }
         int width = 0, nwidth = 0;
         for (int i = u0; i < u1; ++i) { width = std::max(width, units[i].len); nwidth = std::max(nwidth, units[i].nlen); }
-        width = (width + 1) & ~1;  // the kernel walks two slots per trip
         FusedWarp &W = warps[(size_t)w];
         W.width = width;
         W.nwidth = nwidth;
-        W.val_base = (int)(values.size() / 32);
-        values.resize(values.size() + (size_t)width * 32, make_float4(0.f, 0.f, 0.f, 0.f));
-        W.nval_base = (int)(values.size() / 32);
-        values.resize(values.size() + (size_t)nwidth * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+        W.val_base = (int)(values.size() / (H * 32));
+        values.resize(values.size() + (size_t)width * H * 32, make_float4(0.f, 0.f, 0.f, 0.f));
+        W.nval_base = (int)(values.size() / (H * 32));
+        values.resize(values.size() + (size_t)nwidth * H * 32, make_float4(0.f, 0.f, 0.f, 0.f));
         for (int i = u0; i < u1; ++i) {
             const Unit &u = units[i];
             const int l = lane_of[i - u0];
@@ -474,22 +494,30 @@ int build_fused_plan(pvqt *v)
                 const int r = u.local_row + q;
                 for (int e = g.filter_bank.indptr[r]; e < g.filter_bank.indptr[r + 1]; ++e) {
                     const int j = spec + g.filter_bank.indices[e] - lo - u.col0;
-                    float4 &slot = values[((size_t)W.val_base + j) * 32 + l];
-                    (q == 0 ? slot.x : slot.z) = g.filter_bank.data[e].real();
-                    (q == 0 ? slot.y : slot.w) = g.filter_bank.data[e].imag();
+                    float4 &slot = values[(((size_t)W.val_base + j) * H + q / 2) * 32 + l];
+                    ((q & 1) == 0 ? slot.x : slot.z) = g.filter_bank.data[e].real();
+                    ((q & 1) == 0 ? slot.y : slot.w) = g.filter_bank.data[e].imag();
                 }
                 if (u.nlen > 0)
                     for (int e = g.negative_filter_bank.indptr[r]; e < g.negative_filter_bank.indptr[r + 1]; ++e) {
                         const int j = spec + g.negative_filter_bank.indices[e] - lo - u.ncol0;
-                        float4 &slot = values[((size_t)W.nval_base + j) * 32 + l];
+                        float4 &slot = values[(((size_t)W.nval_base + j) * H + q / 2) * 32 + l];
                         // conj(Kneg X) = conj(Kneg) conj(X): keep conj(Kneg)
-                        (q == 0 ? slot.x : slot.z) = g.negative_filter_bank.data[e].real();
-                        (q == 0 ? slot.y : slot.w) = -g.negative_filter_bank.data[e].imag();
+                        ((q & 1) == 0 ? slot.x : slot.z) = g.negative_filter_bank.data[e].real();
+                        ((q & 1) == 0 ? slot.y : slot.w) = -g.negative_filter_bank.data[e].imag();
                     }
             }
         }
     }
-    values.resize(values.size() + (size_t)2 * kFusedRing * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
+    values.resize(values.size() + (size_t)2 * kFusedRing * H * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
+    // Every CTA walks the same coefficients in the same order and the CTAs of a launch run in near lock
+    // step, so a single copy is read through the same few L2 lines by all SMs at once (measured: the kernel
+    // time did not move when its instruction count dropped -- it was waiting on those lines).  A few identical
+    // copies at different addresses spread the requests over the L2 slices; results are unchanged.
+    const uint32_t copies = 16;
+    const size_t one = values.size();
+    values.resize(one * copies);
+    for (uint32_t c = 1; c < copies; ++c) std::copy(values.begin(), values.begin() + (long)one, values.begin() + (long)(one * c));
 
     FusedParams &P = v->fused;
     std::memset(&P, 0, sizeof(P));
@@ -499,11 +527,20 @@ int build_fused_plan(pvqt *v)
     if ((e = upload(v, lane_rows, &P.lane_rows)) != cudaSuccess) return cuda_fail(e, "upload fused lane_rows");
     if ((e = upload(v, values, &P.values)) != cudaSuccess) return cuda_fail(e, "upload fused values");
     P.n_warps = n_warps;
+    P.rows_per_lane = R;
+    P.values_stride = (uint32_t)one;
+    P.values_copies = copies;
     P.n_buckets = (int32_t)v->kernel.n_buckets;
     P.spec_stride = F.spec_stride;
     P.n_cols = n_cols;
+    P.cols_touched = n_cols;
+    for (int w = 0; w < n_warps; ++w)
+        for (int l = 0; l < 32; ++l) {
+            const int4 m = lane_meta[(size_t)w * 32 + l];
+            P.cols_touched = std::max(P.cols_touched, std::max(m.x + warps[(size_t)w].width, m.z + warps[(size_t)w].nwidth));
+        }
     P.ref_db = v->ref_db;
-    if ((e = configure_fused(n_warps, n_cols, P.n_buckets)) != cudaSuccess)
+    if ((e = configure_fused(n_warps, P.cols_touched, P.n_buckets, R)) != cudaSuccess)
         return cuda_fail(e, "configure spmm_db_fused_kernel");
     return PVQT_OK;
 }
@@ -819,21 +856,21 @@ void prof_end(pvqt *v, cudaStream_t stream)
     cudaEventRecord(v->timed.back().b, stream);
 }
 
-// Spectrum / power scratch for up to `frames` frames of one kernel chunk.
-int reserve_scratch(pvqt *v, size_t frames, bool need_power, cudaStream_t stream)
+// Spectrum / power scratch of one launch lane for up to `frames` frames.
+int reserve_scratch(pvqt *v, pvqt::Lane &L, size_t frames, bool need_power, cudaStream_t stream)
 {
     frames = std::min<size_t>(frames, v->chunk_frames);
     const size_t tile_bytes = (size_t)v->fft.spec_stride * kTileFrames * 2 * sizeof(float);
     const size_t want = ((frames + kTileFrames - 1) / kTileFrames) * tile_bytes;
-    if (want > v->spec.bytes) {
-        cudaError_t e = v->spec.reserve(want);
+    if (want > L.spec.bytes) {
+        cudaError_t e = L.spec.reserve(want);
         if (e != cudaSuccess) return cuda_fail(e, "allocate spectrum scratch");
         // frames past the end of the last tile are never written: keep them finite
-        if ((e = cudaMemsetAsync(v->spec.ptr, 0, v->spec.bytes, stream)) != cudaSuccess)
+        if ((e = cudaMemsetAsync(L.spec.ptr, 0, L.spec.bytes, stream)) != cudaSuccess)
             return cuda_fail(e, "clear spectrum scratch");
     }
     if (need_power) {
-        cudaError_t e = v->power.reserve(frames * v->kernel.n_buckets * sizeof(float));
+        cudaError_t e = L.power.reserve(frames * v->kernel.n_buckets * sizeof(float));
         if (e != cudaSuccess) return cuda_fail(e, "allocate power scratch");
     }
     return PVQT_OK;
@@ -853,10 +890,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     const size_t nb = v->kernel.n_buckets;
     const size_t chunk = v->chunk_frames;  // multiple of kTileFrames
     const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
-    if (!d_spec_out) {
-        int rc = reserve_scratch(v, std::min(total, chunk), d_power == nullptr && !v->fused_ok && !v->cluster_ok, stream);
-        if (rc) return rc;
-    }
+    const bool need_power = d_power == nullptr && !v->fused_ok && !v->cluster_ok;
 
     // window groups on the sliding partial-DFT path for this call
     const pvqt::SdftPlan *plan = nullptr;
@@ -877,15 +911,43 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
         return false;
     };
 
+    // Launch ranges: whole streams when a stream is shorter than a chunk, else frame ranges of one stream.  A
+    // single range is cut in n_lanes pieces so that the lanes have something to overlap.
+    struct Range { size_t s0, ns, t0, nf; };
+    std::vector<Range> ranges;
     const bool by_stream = frames_per_stream <= chunk;
-    const size_t streams_per_launch = by_stream ? std::max<size_t>(1, chunk / frames_per_stream) : 1;
-    for (size_t s0 = 0; s0 < n_streams; s0 += streams_per_launch) {
-        const size_t ns = std::min(streams_per_launch, n_streams - s0);
-        for (size_t t0 = 0; t0 < frames_per_stream; t0 += chunk) {
-            const size_t nf = std::min(chunk, frames_per_stream - t0);  // == frames_per_stream when by_stream
+    const int lanes = d_spec_out ? 1 : std::max(1, std::min(v->n_lanes, (int)pvqt::kLanes));
+    if (by_stream && n_streams > 1) {
+        size_t spl = std::max<size_t>(1, chunk / frames_per_stream);
+        if (n_streams <= spl && lanes > 1 && total >= (size_t)lanes * 1024) spl = (n_streams + lanes - 1) / lanes;
+        for (size_t s0 = 0; s0 < n_streams; s0 += spl) ranges.push_back({s0, std::min(spl, n_streams - s0), 0, frames_per_stream});
+    } else {
+        for (size_t s0 = 0; s0 < n_streams; ++s0) {
+            size_t step = chunk;
+            if (frames_per_stream <= chunk && lanes > 1 && frames_per_stream >= (size_t)lanes * 1024)
+                step = ((frames_per_stream + lanes - 1) / lanes + 2 * kTileFrames - 1) / (2 * kTileFrames) * (2 * kTileFrames);
+            for (size_t t0 = 0; t0 < frames_per_stream; t0 += step)
+                ranges.push_back({s0, 1, t0, std::min(step, frames_per_stream - t0)});
+        }
+    }
+    const bool use_lanes = lanes > 1 && ranges.size() > 1;
+    if (use_lanes) {
+        PVQT_CUDA(cudaEventRecord(v->lane_fork, stream));
+        for (int l = 0; l < lanes; ++l) PVQT_CUDA(cudaStreamWaitEvent(v->lane[l].stream, v->lane_fork, 0));
+    }
+    cudaStream_t caller_stream = stream;
+    for (size_t ri = 0; ri < ranges.size(); ++ri) {
+        {
+            const size_t s0 = ranges[ri].s0, ns = ranges[ri].ns, t0 = ranges[ri].t0, nf = ranges[ri].nf;
+            pvqt::Lane &L = v->lane[use_lanes ? ri % (size_t)lanes : 0];
+            stream = use_lanes ? L.stream : caller_stream;
+            if (!d_spec_out) {
+                int rc = reserve_scratch(v, L, ns * nf, need_power, stream);
+                if (rc) return rc;
+            }
             const size_t f0 = s0 * frames_per_stream + t0;               // flat index of the launch's first frame
             const uint32_t n = (uint32_t)(ns * nf);
-            float *spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(v->spec.ptr);
+            float *spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(L.spec.ptr);
 
             // ---- K-sdft partial sums ----
             std::vector<SdftParams> sd;
@@ -907,12 +969,12 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             if (!sd.empty()) {
                 size_t need = 0;
                 for (const auto &sp : sd) need += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
-                if (v->sdft_c.reserve(need) != cudaSuccess || v->sdft_r.reserve(need) != cudaSuccess)
+                if (L.sdft_c.reserve(need) != cudaSuccess || L.sdft_r.reserve(need) != cudaSuccess)
                     return cuda_fail(cudaGetLastError(), "allocate K-sdft scratch");
                 size_t off = 0;
                 for (auto &sp : sd) {
-                    sp.partial_c = reinterpret_cast<float2 *>(static_cast<char *>(v->sdft_c.ptr) + off);
-                    sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(v->sdft_r.ptr) + off);
+                    sp.partial_c = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_c.ptr) + off);
+                    sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_r.ptr) + off);
                     off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                     prof_begin(v, 4, stream);
                     cudaError_t e = launch_sdft_partial(sp, stream);
@@ -998,7 +1060,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             sp.n_frames = n;
             sp.n_tiles = (n + kTileFrames - 1) / kTileFrames;
             sp.spec = spec;
-            sp.power = d_power ? d_power + f0 * nb : static_cast<float *>(v->power.ptr);
+            sp.power = d_power ? d_power + f0 * nb : static_cast<float *>(L.power.ptr);
             prof_begin(v, 1, stream);
             e = launch_spmm(sp, stream);
             if (e != cudaSuccess) return cuda_fail(e, "launch spmm_kernel");
@@ -1018,6 +1080,11 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             v->launches.fetch_add(1);
         }
     }
+    if (use_lanes)
+        for (int l = 0; l < lanes; ++l) {
+            PVQT_CUDA(cudaEventRecord(v->lane[l].done, v->lane[l].stream));
+            PVQT_CUDA(cudaStreamWaitEvent(caller_stream, v->lane[l].done, 0));
+        }
     return PVQT_OK;
 }
 
@@ -1167,8 +1234,9 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         const size_t frames = n_streams * frames_per_stream;
         PVQT_CUDA(v->d_audio.reserve(audio_samples * sizeof(float)));
         PVQT_CUDA(v->d_out.reserve(frames * J.nb * sizeof(float)));
-        int rc = reserve_scratch(v, frames, !v->fused_ok && !v->cluster_ok, v->stream);
-        if (rc) return rc;
+        int rc = PVQT_OK;
+        for (auto &L : v->lane)
+            if ((rc = reserve_scratch(v, L, frames, !v->fused_ok && !v->cluster_ok, v->stream)) != PVQT_OK) return rc;
         auto enqueue = [&]() -> int {
             int r = fork_streams(v, ev);
             if (r) return r;
@@ -1180,8 +1248,9 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         pvqt::HostCallKey key;
         key.audio = audio; key.out = out; key.n_streams = n_streams; key.stream_stride = stream_stride;
         key.n_samples = n_samples; key.hop = hop; key.frames_per_stream = frames_per_stream;
-        key.generations = v->d_audio.generation * 1000003u + v->d_out.generation * 10007u + v->spec.generation * 101u +
-                          v->power.generation + v->sdft_c.generation * 7u + v->sdft_r.generation * 13u;
+        key.generations = v->d_audio.generation * 1000003u + v->d_out.generation * 10007u;
+        for (const auto &L : v->lane)
+            key.generations += L.spec.generation * 101u + L.power.generation + L.sdft_c.generation * 7u + L.sdft_r.generation * 13u;
         if (v->use_graphs && !v->profiling) {
             if (!(v->graph_exec && key == v->graph_key)) {
                 if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
@@ -1399,6 +1468,13 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
         (e = cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking)) != cudaSuccess)
         return cuda_error(e, "cudaStreamCreate");
 
+    for (auto &L : v->lane)
+        if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
+            return cuda_error(e, "create launch lanes");
+    if ((e = cudaEventCreateWithFlags(&v->lane_fork, cudaEventDisableTiming)) != cudaSuccess)
+        return cuda_error(e, "create launch lanes");
+    if (const char *s = std::getenv("PVQT_LANES")) v->n_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
     if (const char *s = std::getenv("PVQT_SEGMENTS")) v->segments_per_batch = std::max(1, std::atoi(s));
     if (const char *s = std::getenv("PVQT_GRAPHS")) v->use_graphs = std::atoi(s) != 0;
     pvqt *raw = v.release();
@@ -1424,10 +1500,12 @@ void pvqt_destroy(pvqt *v)
     if (v->graph_exec) cudaGraphExecDestroy(v->graph_exec);
     for (const auto &t : v->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (void *p : v->owned) cudaFree(p);
-    v->spec.release();
-    v->power.release();
-    v->sdft_c.release();
-    v->sdft_r.release();
+    for (auto &L : v->lane) {
+        if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+        if (L.done) cudaEventDestroy(L.done);
+        L.spec.release(); L.power.release(); L.sdft_c.release(); L.sdft_r.release();
+    }
+    if (v->lane_fork) cudaEventDestroy(v->lane_fork);
     v->d_audio.release();
     v->d_out.release();
     delete v;

@@ -27,7 +27,7 @@ __device__ __forceinline__ void cp_async4_zfill(void *smem_dst, const void *gmem
 // block the packed FFMA2 lanes hold the even / odd samples' contributions -- both operands are natural
 // register pairs: two consecutive samples of one LDS.128 and the matching pair of B twiddles -- added at
 // the end of the block, times A[a], into the chunk's running sum.  All f32; the long sum over chunks is
-// compensated (Kahan) in the combine step, which is where the accuracy of the path is decided.
+// split over four interleaved partial sums in the combine step (sdft_combine.cuh).
 __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __grid_constant__ SdftParams P)
 {
     extern __shared__ __align__(16) float4 sdft_smem[];

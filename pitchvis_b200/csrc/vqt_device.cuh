@@ -111,7 +111,7 @@ struct FftParams {
 // shared memory of the stand-alone combine kernel: the chunk rows of one 8-frame tile
 __host__ __device__ inline size_t sdft_combine_smem_bytes_dev(int q, int nk)
 {
-    return (size_t)(q + kTileFrames) * nk * sizeof(float2);  // + 1 row: alignment slack
+    return (size_t)(2 * q + 2 * kTileFrames + 2) * nk * sizeof(float2);  // C rows, R rows, phase table, slack
 }
 
 constexpr int kSdftThreads = 256;     // 4 row groups x 2 bin halves (64 bins per CTA)
@@ -170,12 +170,16 @@ struct FusedWarp {
 struct FusedParams {
     const FusedWarp *warps;
     const int4   *lane_meta;   // [warp][lane]: (col0, len, ncol0, nlen) in spectrum columns
-    const int2   *lane_rows;   // [warp][lane]: (first output row, valid rows 0..2)
-    const float4 *values;      // [slot][lane]: (K[row0].re, K[row0].im, K[row1].re, K[row1].im)
+    const int2   *lane_rows;   // [warp][lane]: (first output row, valid rows 0..rows_per_lane)
+    const float4 *values;      // [copy][slot][row pair][lane]: (K[row0].re, K[row0].im, K[row1].re, K[row1].im)
+    uint32_t values_stride;    // float4 entries per copy
+    uint32_t values_copies;    // identical copies: CTA b streams copy b % copies (see build_fused_plan)
     int32_t  n_warps;
+    int32_t  rows_per_lane;    // 2 or 4 adjacent kernel rows per lane
     int32_t  n_buckets;
     int32_t  spec_stride;      // columns per tile
     int32_t  n_cols;           // columns staged per tile (<= spec_stride)
+    int32_t  cols_touched;     // columns the band walk may read (>= n_cols; the excess is zero-filled)
     uint32_t n_frames;
     uint32_t n_tiles;
     const float *spec;         // tiled planar layout
@@ -234,12 +238,6 @@ constexpr int kClusterThreads = 384;     // 12 warps: up to 96 row pairs per par
 constexpr int kClusterRoundFrames = 2 * kTileFrames;
 
 constexpr int kFusedRing = 4;   // coefficient slots the one-CTA-per-tile K-spmm-db keeps in flight per lane
-// float4 entries of its staging / log-spectrum region: max(n_cols records of 64 bytes, ls[8][n_buckets])
-__host__ __device__ inline int fused_stage_f4(int n_cols, int n_buckets)
-{
-    const int stage = n_cols * 4, ls = (kTileFrames * n_buckets + 3) / 4;
-    return stage > ls ? stage : ls;
-}
 constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
 constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
 
@@ -257,9 +255,9 @@ cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream);
 size_t      cluster_smem_bytes(int coef_bytes, int max_rows, int cluster_size);
 cudaError_t configure_cluster(int coef_bytes, int max_rows, int cluster_size, int *max_clusters);
 cudaError_t launch_spmm_db_cluster(const ClusterParams &p, int n_clusters, cudaStream_t stream);
-bool        fused_supported(int n_warps, int n_cols, int n_buckets);
-size_t      fused_smem_bytes(int n_cols, int n_buckets, int n_warps);
-cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets);
+bool        fused_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane);
+size_t      fused_smem_bytes(int cols_touched, int n_buckets, int n_warps, int rows_per_lane);
+cudaError_t configure_fused(int n_warps, int cols_touched, int n_buckets, int rows_per_lane);
 cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);
 size_t spmm_smem_bytes(int max_cols);

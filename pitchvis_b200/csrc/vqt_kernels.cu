@@ -502,26 +502,38 @@ __global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid
 // the CTA owns all n_buckets rows of its frames the frame-wise max / min of power_to_db (vqt.rs:933-940)
 // are reduced in shared memory: the dB values are written once, coalesced, and the |z|^2 round trip
 // through HBM/L2 and the third launch disappear.
-template <int MAX_THREADS, int MIN_BLOCKS>
+// The tile is staged de-swizzled into four planes [chunk][column] of 16-byte entries (PLANE columns each, a
+// compile-time stride), so a lane's four spectrum loads are one pointer plus immediates; band slots past a
+// row's own band carry zero coefficients and columns past the staged range are zero-filled, so the band
+// walk has no predicates at all (profiles/r01_e: the address arithmetic, predicates and register clears
+// of the swizzled, predicated form were 58 of the 90 instructions per slot).
+template <int MAX_THREADS, int MIN_BLOCKS, int PLANE, int ROWS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(const __grid_constant__ FusedParams P)
 {
+    constexpr int H = ROWS / 2;      // float4 coefficient entries per lane and slot (two rows each)
+    constexpr int RING = kFusedRing;
     extern __shared__ __align__(16) float4 fused_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
     const FusedWarp W = P.warps[warp];
     const int4 meta = __ldg(P.lane_meta + warp * 32 + lane);
     const int2 rows = __ldg(P.lane_rows + warp * 32 + lane);
-    const float4 *kv = P.values + (size_t)W.val_base * 32 + lane;
-    const float4 *nv = P.values + (size_t)W.nval_base * 32 + lane;
-    // The coefficient stream goes through a lane-private ring in shared memory filled with cp.async
-    // kFusedRing slots ahead: a register prefetch deep enough to cover the L2 latency does not fit the
-    // 64-register budget of three resident CTAs (profiles/r01_d: the wait on that load was 26 % of all stall
-    // samples).  Lane l copies and reads only its own 16 bytes of a slot, so no warp-level sync is needed.
-    float4 *ring = fused_smem + fused_stage_f4(P.n_cols, P.n_buckets) + (size_t)warp * kFusedRing * 32 + lane;
+    const float4 *values = P.values + (size_t)(tile % P.values_copies) * P.values_stride;
+    const float4 *kv = values + (size_t)W.val_base * (H * 32) + lane;
+    // The coefficient stream goes through a lane-private ring in shared memory filled with cp.async RING slots
+    // ahead: a register prefetch deep enough to cover the L2 latency does not fit the register budget of three
+    // resident CTAs.  Lane l copies and reads only its own 16-byte entries, so no warp-level sync is needed.
+    float4 *ring = fused_smem + 4 * PLANE + (size_t)warp * (RING * H * 32) + lane;
 #pragma unroll
-    for (int s = 0; s < kFusedRing; ++s) {  // `values` ends with kFusedRing spare slots
-        cp_async16(ring + s * 32, kv + s * 32);
+    for (int s = 0; s < RING; ++s) {  // `values` ends with spare slots
+#pragma unroll
+        for (int h = 0; h < H; ++h) cp_async16(ring + (s * H + h) * 32, kv + (s * H + h) * 32);
         asm volatile("cp.async.commit_group;\n" ::);
+    }
+    {   // columns the band walk may touch past the staged range
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < 4 * (P.cols_touched - P.n_cols); i += blockDim.x)
+            fused_smem[(i & 3) * PLANE + P.n_cols + (i >> 2)] = z;
     }
 
     pdl_launch_dependents();
@@ -529,71 +541,81 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.spec) + (size_t)tile * P.spec_stride * 4;
         const int n16 = P.n_cols * 4;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) cp_async16(fused_smem + i, src + i);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+            const int c = i >> 2, p = i & 3;     // physical chunk p of column c
+            const int q = p ^ ((c >> 1) & 3);    // logical chunk: 0,1 = Re frames 0-3, 4-7; 2,3 = Im
+            cp_async16(fused_smem + q * PLANE + c, src + i);
+        }
     }
     cp_async_wait_all();
     __syncthreads();
 
-    float2 re0[4], im0[4], re1[4], im1[4];
+    float2 re[ROWS][4], im[ROWS][4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) re0[p] = im0[p] = re1[p] = im1[p] = make_float2(0.f, 0.f);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) re[r][p] = im[r][p] = make_float2(0.f, 0.f);
 
-#pragma unroll 1
-    for (int j = 0; j < W.width; ++j) {
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(kFusedRing - 1));  // slot j has landed
-        float4 *slot = ring + (j & (kFusedRing - 1)) * 32;
-        const float4 k = *slot;
-        cp_async16(slot, kv + (j + kFusedRing) * 32);
+    // One ring pass over the warp's slots: the band (y += K x), then the conjugate-part band (y += conj(Kneg x)),
+    // whose slots follow the band's in `values` -- so its coefficients ride the same prefetch instead of paying a
+    // dependent L2 / DRAM round trip per slot at the end of every CTA's critical path (profiles/r01_g: 12 us).
+    auto next_slot = [&](int j, float4 (&k)[H]) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(RING - 1));  // slot j has landed
+        float4 *slot = ring + (j & (RING - 1)) * (H * 32);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            k[h] = slot[h * 32];
+            cp_async16(slot + h * 32, kv + ((j + RING) * H + h) * 32);
+        }
         asm volatile("cp.async.commit_group;\n" ::);
-        const int c = meta.x + j;
-        const float4 *rec = fused_smem + c * 4;
-        const int sw = (c >> 1) & 3;
-        float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
-        if (j < meta.y) {
-            xr03 = rec[sw];
-            xr47 = rec[1 ^ sw];
-            xi03 = rec[2 ^ sw];
-            xi47 = rec[3 ^ sw];
+    };
+    {
+        const float4 *xp = fused_smem + meta.x;
+#pragma unroll 1
+        for (int j = 0; j < W.width; ++j) {
+            float4 k[H];
+            next_slot(j, k);
+            const float4 xr03 = xp[0], xr47 = xp[PLANE], xi03 = xp[2 * PLANE], xi47 = xp[3 * PLANE];
+            ++xp;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mac8<false>(re[2 * h], im[2 * h], k[h].x, k[h].y, xr03, xr47, xi03, xi47);
+                mac8<false>(re[2 * h + 1], im[2 * h + 1], k[h].z, k[h].w, xr03, xr47, xi03, xi47);
+            }
         }
-        mac8<false>(re0, im0, k.x, k.y, xr03, xr47, xi03, xi47);
-        mac8<false>(re1, im1, k.z, k.w, xr03, xr47, xi03, xi47);
     }
-    for (int j = 0; j < W.nwidth; ++j) {
-        const float4 k = __ldg(nv + j * 32);  // conj(Kneg), see device plan
-        const int c = meta.z + j;
-        const float4 *rec = fused_smem + c * 4;
-        const int sw = (c >> 1) & 3;
-        float4 xr03 = zero4, xr47 = zero4, xi03 = zero4, xi47 = zero4;
-        if (j < meta.w) {
-            xr03 = rec[sw];
-            xr47 = rec[1 ^ sw];
-            xi03 = rec[2 ^ sw];
-            xi47 = rec[3 ^ sw];
+    {
+        const float4 *xp = fused_smem + meta.z;
+#pragma unroll 1
+        for (int j = W.width; j < W.width + W.nwidth; ++j) {
+            float4 k[H];  // conj(Kneg), see device plan
+            next_slot(j, k);
+            const float4 xr03 = xp[0], xr47 = xp[PLANE], xi03 = xp[2 * PLANE], xi47 = xp[3 * PLANE];
+            ++xp;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mac8<true>(re[2 * h], im[2 * h], k[h].x, k[h].y, xr03, xr47, xi03, xi47);
+                mac8<true>(re[2 * h + 1], im[2 * h + 1], k[h].z, k[h].w, xr03, xr47, xi03, xi47);
+            }
         }
-        mac8<true>(re0, im0, k.x, k.y, xr03, xr47, xi03, xi47);
-        mac8<true>(re1, im1, k.z, k.w, xr03, xr47, xi03, xi47);
     }
 
     // |z|^2 (norm_sqr) and log_spec (vqt.rs:930) per lane; the staging buffer becomes ls[frame][row]
-    const float pr0[kTileFrames] = {re0[0].x, re0[0].y, re0[1].x, re0[1].y, re0[2].x, re0[2].y, re0[3].x, re0[3].y};
-    const float pi0[kTileFrames] = {im0[0].x, im0[0].y, im0[1].x, im0[1].y, im0[2].x, im0[2].y, im0[3].x, im0[3].y};
-    const float pr1[kTileFrames] = {re1[0].x, re1[0].y, re1[1].x, re1[1].y, re1[2].x, re1[2].y, re1[3].x, re1[3].y};
-    const float pi1[kTileFrames] = {im1[0].x, im1[0].y, im1[1].x, im1[1].y, im1[2].x, im1[2].y, im1[3].x, im1[3].y};
     const uint32_t frame0 = tile * kTileFrames;
     const int nb = P.n_buckets;
     __syncthreads();  // every warp is done reading the staged spectrum
     float *ls = reinterpret_cast<float *>(fused_smem);
 #pragma unroll
-    for (int f = 0; f < kTileFrames; ++f) {
-        const float p0 = pr0[f] * pr0[f] + pi0[f] * pi0[f];
-        const float p1 = pr1[f] * pr1[f] + pi1[f] * pi1[f];
-        if (rows.y > 0) ls[f * nb + rows.x] = log_spec(p0, P.ref_db);
-        if (rows.y > 1) ls[f * nb + rows.x + 1] = log_spec(p1, P.ref_db);
-        if (P.power != nullptr && frame0 + f < P.n_frames) {
-            float *pw = P.power + (size_t)(frame0 + f) * nb + rows.x;
-            if (rows.y > 0) pw[0] = p0;
-            if (rows.y > 1) pw[1] = p1;
+    for (int r = 0; r < ROWS; ++r) {
+        if (rows.y > r) {
+#pragma unroll
+            for (int f = 0; f < kTileFrames; ++f) {
+                const float zr = (f & 1) ? re[r][f >> 1].y : re[r][f >> 1].x;
+                const float zi = (f & 1) ? im[r][f >> 1].y : im[r][f >> 1].x;
+                const float p = zr * zr + zi * zi;
+                ls[f * nb + rows.x + r] = log_spec(p, P.ref_db);
+                if (P.power != nullptr && frame0 + f < P.n_frames) P.power[(size_t)(frame0 + f) * nb + rows.x + r] = p;
+            }
         }
     }
     __syncthreads();
@@ -711,39 +733,64 @@ cudaError_t launch_spmm(const SpmmParams &p, cudaStream_t stream)
 }
 
 // ---- K-spmm-db launch -------------------------------------------------------------------------
-size_t fused_smem_bytes(int n_cols, int n_buckets, int n_warps)
+// plane width (columns) of the staged tile: the smallest instantiated width that holds `cols_touched`
+int fused_plane_cols(int cols_touched)
 {
-    return (size_t)fused_stage_f4(n_cols, n_buckets) * sizeof(float4) + (size_t)n_warps * kFusedRing * 32 * sizeof(float4);
+    for (int p : {832, 1664})
+        if (cols_touched <= p) return p;
+    return 0;
 }
 
-bool fused_supported(int n_warps, int n_cols, int n_buckets)
+size_t fused_smem_bytes(int cols_touched, int n_buckets, int n_warps, int rows_per_lane)
 {
-    return n_warps >= 1 && n_warps <= 32 && fused_smem_bytes(n_cols, n_buckets, n_warps) <= 200 * 1024;
+    const size_t plane = (size_t)4 * fused_plane_cols(cols_touched) * sizeof(float4);
+    const size_t ls = (size_t)kTileFrames * n_buckets * sizeof(float);
+    return std::max(plane, (ls + 15) & ~(size_t)15) +
+           (size_t)n_warps * kFusedRing * (rows_per_lane / 2) * 32 * sizeof(float4);
+}
+
+bool fused_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane)
+{
+    const int max_warps = rows_per_lane == 4 ? 16 : 32;
+    return n_warps >= 1 && n_warps <= max_warps && fused_plane_cols(cols_touched) > 0 &&
+           (size_t)kTileFrames * n_buckets * sizeof(float) <= (size_t)4 * fused_plane_cols(cols_touched) * sizeof(float4) &&
+           fused_smem_bytes(cols_touched, n_buckets, n_warps, rows_per_lane) <= 200 * 1024;
 }
 
 namespace {
 template <typename Fn>
-cudaError_t with_fused_kernel(int n_warps, Fn fn)
+cudaError_t with_fused_kernel(int n_warps, int plane, int rows_per_lane, Fn fn)
 {
-    // register budget: 3 resident CTAs of <= 10 warps (64 registers), 2 of <= 16, 1 beyond
-    if (n_warps <= 10) return fn(spmm_db_fused_kernel<320, 3>);
-    if (n_warps <= 16) return fn(spmm_db_fused_kernel<512, 2>);
-    return fn(spmm_db_fused_kernel<1024, 1>);
+    if (rows_per_lane == 4) {   // 128 registers: three resident CTAs of <= 5 warps, one of <= 16
+        if (plane == 832) {
+            if (n_warps <= 5) return fn(spmm_db_fused_kernel<160, 3, 832, 4>);
+            return fn(spmm_db_fused_kernel<512, 1, 832, 4>);
+        }
+        return fn(spmm_db_fused_kernel<512, 1, 1664, 4>);
+    }
+    // two rows per lane, 64 registers: 3 resident CTAs of <= 10 warps, 2 of <= 16, 1 beyond
+    if (plane == 832) {
+        if (n_warps <= 10) return fn(spmm_db_fused_kernel<320, 3, 832, 2>);
+        if (n_warps <= 16) return fn(spmm_db_fused_kernel<512, 2, 832, 2>);
+        return fn(spmm_db_fused_kernel<1024, 1, 832, 2>);
+    }
+    if (n_warps <= 16) return fn(spmm_db_fused_kernel<512, 1, 1664, 2>);
+    return fn(spmm_db_fused_kernel<1024, 1, 1664, 2>);
 }
 }  // namespace
 
-cudaError_t configure_fused(int n_warps, int n_cols, int n_buckets)
+cudaError_t configure_fused(int n_warps, int cols_touched, int n_buckets, int rows_per_lane)
 {
-    const int smem = (int)fused_smem_bytes(n_cols, n_buckets, n_warps);
-    return with_fused_kernel(n_warps, [&](auto kernel) {
+    const int smem = (int)fused_smem_bytes(cols_touched, n_buckets, n_warps, rows_per_lane);
+    return with_fused_kernel(n_warps, fused_plane_cols(cols_touched), rows_per_lane, [&](auto kernel) {
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     });
 }
 
 cudaError_t launch_spmm_db_fused(const FusedParams &p, cudaStream_t stream)
 {
-    const size_t smem = fused_smem_bytes(p.n_cols, p.n_buckets, p.n_warps);
-    return with_fused_kernel(p.n_warps, [&](auto kernel) {
+    const size_t smem = fused_smem_bytes(p.cols_touched, p.n_buckets, p.n_warps, p.rows_per_lane);
+    return with_fused_kernel(p.n_warps, fused_plane_cols(p.cols_touched), p.rows_per_lane, [&](auto kernel) {
         return launch_dependent(kernel, p.n_tiles, (unsigned)p.n_warps * 32, smem, stream, p);
     });
 }

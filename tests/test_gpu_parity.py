@@ -157,7 +157,8 @@ def test_power_parity_above_minus_80_db(vqt, oracle_default, chords):
     # and the dB epilogue applied by the oracle to the GPU's own power reproduces the GPU output
     db_gpu = d_out.download((n_frames, 588))
     db_from_pow = np.stack([orc.power_to_db(p_gpu[t]) for t in range(n_frames)])
-    assert np.abs(db_gpu - db_from_pow).max() <= 2e-5
+    # (the device takes 10 log10 as 3.0103 * lg2.approx: <= 3e-5 dB, device_helpers.cuh)
+    assert np.abs(db_gpu - db_from_pow).max() <= 6e-5
 
 
 def test_spmm_db_variants_agree(vqt, oracle_default, chords):
