@@ -58,6 +58,12 @@ def workload(name: str, seed: int):
     return params, audio, hop, n_frames
 
 
+def workload_name(name: str, hop: int, n_frames: int) -> str:
+    which = "BASELINE.json configs[1]" if name == "chords60" else "BASELINE.json configs[3]"
+    return (f"{name}: 60 s synthetic polyphonic audio per GPU (random chords, seed = rank), hop {hop}, "
+            f"{n_frames} frames/step/GPU ({which})")
+
+
 def oracle_params(name: str):
     import orc
     return orc.default_params() if name == "chords60" else orc.hires_params()
@@ -150,7 +156,8 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: 60 s synthetic polyphonic audio, hop {hop}, {n_frames} frames/step"},
+        "config": {"workload": workload_name(args.workload, hop, n_frames),
+                   "sample": "every step transforms all frames of the workload on the host cores (oracle f32 path)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} passes over all {n_frames} frames of the workload, "
                                    "oracle f32 path (C port of vqt.rs:866-954; the Rust crate cannot be built here)"},
@@ -338,8 +345,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: 60 s synthetic polyphonic audio per GPU (random chords, seed = rank), "
-                            f"default hop {hop}, {n_frames} frames/step/GPU (BASELINE.json configs[1])",
+                "workload": workload_name(args.workload, hop, n_frames),
                 "n_fft": params.n_fft, "n_buckets": nb, "hop": hop, "frames_per_step_per_gpu": n_frames,
                 "l2": f"flushed between timed steps ({flush_bytes >> 20} MiB memset"
                       + (" followed by a read sweep of the same buffer, so the flush leaves no dirty lines)"

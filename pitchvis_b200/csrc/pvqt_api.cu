@@ -155,6 +155,7 @@ struct pvqt {
         DeviceBuffer spec, power, sdft_c, sdft_r;
     } lane[kLanes];
     cudaEvent_t lane_fork = nullptr;
+    int host_lanes = 2;  // compute lanes of the pipelined host entries (PVQT_HOST_LANES)
     int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames
     DeviceBuffer d_audio, d_out;
     std::atomic<uint64_t> launches{0};
@@ -881,7 +882,8 @@ int reserve_scratch(pvqt *v, pvqt::Lane &L, size_t frames, bool need_power, cuda
 // every arrow a programmatic dependent launch.  Work is cut into launches of at most chunk_frames frames:
 // whole streams when a stream is shorter than that, else frame ranges of one stream.
 int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_stride, size_t hop,
-               size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream)
+               size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream,
+               int scratch_lane = 0)
 {
     const size_t total = n_streams * frames_per_stream;
     if (total == 0) return PVQT_OK;
@@ -939,7 +941,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     for (size_t ri = 0; ri < ranges.size(); ++ri) {
         {
             const size_t s0 = ranges[ri].s0, ns = ranges[ri].ns, t0 = ranges[ri].t0, nf = ranges[ri].nf;
-            pvqt::Lane &L = v->lane[use_lanes ? ri % (size_t)lanes : 0];
+            pvqt::Lane &L = v->lane[use_lanes ? ri % (size_t)lanes : (size_t)scratch_lane];
             stream = use_lanes ? L.stream : caller_stream;
             if (!d_spec_out) {
                 int rc = reserve_scratch(v, L, ns * nf, need_power, stream);
@@ -1130,6 +1132,8 @@ int fork_streams(pvqt *v, EventPool &ev)
     PVQT_CUDA(cudaEventRecord(fork, v->stream));
     PVQT_CUDA(cudaStreamWaitEvent(v->s_in, fork, 0));
     PVQT_CUDA(cudaStreamWaitEvent(v->s_out, fork, 0));
+    if (v->host_lanes > 1)
+        for (int l = 0; l < v->host_lanes; ++l) PVQT_CUDA(cudaStreamWaitEvent(v->lane[l].stream, fork, 0));
     return PVQT_OK;
 }
 
@@ -1141,18 +1145,29 @@ int join_streams(pvqt *v, EventPool &ev)
         PVQT_CUDA(cudaEventRecord(j, s));
         PVQT_CUDA(cudaStreamWaitEvent(v->stream, j, 0));
     }
+    if (v->host_lanes > 1)
+        for (int l = 0; l < v->host_lanes; ++l) {
+            cudaEvent_t j;
+            PVQT_CUDA(ev.next(&j));
+            PVQT_CUDA(cudaEventRecord(j, v->lane[l].stream));
+            PVQT_CUDA(cudaStreamWaitEvent(v->stream, j, 0));
+        }
     return PVQT_OK;
 }
 
 int compute_and_copy_out(pvqt *v, EventPool &ev, const HostJob &J, cudaEvent_t copied, const float *d_audio, size_t ns,
-                         size_t dstride, size_t nf, float *d_out, float *h_out)
+                         size_t dstride, size_t nf, float *d_out, float *h_out, size_t segment)
 {
-    PVQT_CUDA(cudaStreamWaitEvent(v->stream, copied, 0));
-    int rc = run_device(v, d_audio, ns, dstride, J.hop, nf, d_out, nullptr, nullptr, v->stream);
+    // consecutive segments compute on alternating lanes (stream + scratch): the kernels of a segment are
+    // latency-bound at these sizes, so two segments in flight keep the device-to-host copies fed
+    const int lane = v->host_lanes > 1 ? (int)(segment % (size_t)v->host_lanes) : 0;
+    cudaStream_t cs = v->host_lanes > 1 ? v->lane[lane].stream : v->stream;
+    PVQT_CUDA(cudaStreamWaitEvent(cs, copied, 0));
+    int rc = run_device(v, d_audio, ns, dstride, J.hop, nf, d_out, nullptr, nullptr, cs, lane);
     if (rc) return rc;
     cudaEvent_t done;
     PVQT_CUDA(ev.next(&done));
-    PVQT_CUDA(cudaEventRecord(done, v->stream));
+    PVQT_CUDA(cudaEventRecord(done, cs));
     PVQT_CUDA(cudaStreamWaitEvent(v->s_out, done, 0));
     PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * J.nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
     return PVQT_OK;
@@ -1173,7 +1188,7 @@ int enqueue_stream_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t b0, si
         PVQT_CUDA(cudaEventRecord(copied, v->s_in));
         int rc = compute_and_copy_out(v, ev, J, copied, d_audio + s0 * dstride, ns, dstride, J.frames_per_stream,
                                       d_out + s0 * J.frames_per_stream * J.nb,
-                                      J.out + (b0 + s0) * J.frames_per_stream * J.nb);
+                                      J.out + (b0 + s0) * J.frames_per_stream * J.nb, s0 / per_seg);
         if (rc) return rc;
     }
     return PVQT_OK;
@@ -1198,7 +1213,7 @@ int enqueue_frame_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t s, size
         PVQT_CUDA(ev.next(&copied));
         PVQT_CUDA(cudaEventRecord(copied, v->s_in));
         int rc = compute_and_copy_out(v, ev, J, copied, d_audio + f0 * J.hop, 1, 0, nf, d_out + f0 * J.nb,
-                                      J.out + (s * J.frames_per_stream + b0 + f0) * J.nb);
+                                      J.out + (s * J.frames_per_stream + b0 + f0) * J.nb, f0 / per_seg);
         if (rc) return rc;
     }
     return PVQT_OK;
@@ -1475,6 +1490,7 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
     if ((e = cudaEventCreateWithFlags(&v->lane_fork, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_error(e, "create launch lanes");
     if (const char *s = std::getenv("PVQT_LANES")) v->n_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
+    if (const char *s = std::getenv("PVQT_HOST_LANES")) v->host_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
     if (const char *s = std::getenv("PVQT_SEGMENTS")) v->segments_per_batch = std::max(1, std::atoi(s));
     if (const char *s = std::getenv("PVQT_GRAPHS")) v->use_graphs = std::atoi(s) != 0;
     pvqt *raw = v.release();
