@@ -379,9 +379,9 @@ int build_device_plan(pvqt *v)
 // ---- K-spmm-db plan: row pairs sorted by band length, dealt to warps, bank-conflict-free lanes ----
 int build_fused_plan(pvqt *v)
 {
-    // rows per lane: 4 shares every spectrum load between four kernel rows (half the shared-memory traffic per
-    // FMA of 2; the band walk is co-limited by the LDS and FMA pipes, profiles/r01_f); PVQT_ROWS_PER_LANE=2 keeps
-    // the two-row form for comparison.
+    // rows per lane: 4 would share every spectrum load between four kernel rows (half the shared-memory traffic per
+    // FMA of 2) but leaves 5 warps per CTA: measured 68 us against 38 us on B200 (DESIGN.md, K-spmm-db), so 2 is
+    // the default and PVQT_ROWS_PER_LANE=4 selects the four-row form.
     int R = 2;
     if (const char *e = std::getenv("PVQT_ROWS_PER_LANE")) R = std::atoi(e) == 4 ? 4 : 2;
     const int H = R / 2;
@@ -511,11 +511,10 @@ int build_fused_plan(pvqt *v)
         }
     }
     values.resize(values.size() + (size_t)2 * kFusedRing * H * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
-    // Every CTA walks the same coefficients in the same order and the CTAs of a launch run in near lock
-    // step, so a single copy is read through the same few L2 lines by all SMs at once (measured: the kernel
-    // time did not move when its instruction count dropped -- it was waiting on those lines).  A few identical
-    // copies at different addresses spread the requests over the L2 slices; results are unchanged.
-    const uint32_t copies = 16;
+    // Every CTA walks the same coefficients in the same order; identical copies at different addresses (CTA b
+    // streams copy b % copies) would spread the requests over more L2 slices.  Measured with 16 copies on B200:
+    // no change (DESIGN.md, K-spmm-db), so one copy is kept; the mechanism stays for larger kernels.
+    const uint32_t copies = 1;
     const size_t one = values.size();
     values.resize(one * copies);
     for (uint32_t c = 1; c < copies; ++c) std::copy(values.begin(), values.begin() + (long)one, values.begin() + (long)(one * c));

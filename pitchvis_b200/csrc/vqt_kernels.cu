@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kDbWarps * 32) power_to_db_kernel(const __grid
 // The tile is staged de-swizzled into four planes [chunk][column] of 16-byte entries (PLANE columns each, a
 // compile-time stride), so a lane's four spectrum loads are one pointer plus immediates; band slots past a
 // row's own band carry zero coefficients and columns past the staged range are zero-filled, so the band
-// walk has no predicates at all (profiles/r01_e: the address arithmetic, predicates and register clears
+// walk has no predicates at all (ncu source page: the address arithmetic, predicates and register clears
 // of the swizzled, predicated form were 58 of the 90 instructions per slot).
 template <int MAX_THREADS, int MIN_BLOCKS, int PLANE, int ROWS>
 __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(const __grid_constant__ FusedParams P)
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
 
     // One ring pass over the warp's slots: the band (y += K x), then the conjugate-part band (y += conj(Kneg x)),
     // whose slots follow the band's in `values` -- so its coefficients ride the same prefetch instead of paying a
-    // dependent L2 / DRAM round trip per slot at the end of every CTA's critical path (profiles/r01_g: 12 us).
+    // dependent L2 / DRAM round trip per slot at the end of every CTA's critical path.
     auto next_slot = [&](int j, float4 (&k)[H]) {
         asm volatile("cp.async.wait_group %0;\n" ::"n"(RING - 1));  // slot j has landed
         float4 *slot = ring + (j & (RING - 1)) * (H * 32);
