@@ -100,6 +100,15 @@ int  pvqt_analysis_preprocess_device(pvqt_analysis *a, const float *d_db, size_t
                                      uint64_t frame_time_ns, const pvqt_analysis_outputs *d_out, void *cuda_stream);
 int  pvqt_analysis_synchronize(pvqt_analysis *a);
 
+/* ---- chroma reduction ------------------------------------------------------
+ * pitchvis_viewer/src/display_system/update.rs:1104-1131: per frame, the sum of 10^(dB/10) per pitch class (bin b
+ * belongs to class (round(12 b / buckets_per_octave) + class of min_freq relative to C4 = 261.626 Hz) mod 12),
+ * divided by the largest of the 12 sums when that is positive.  The reference feeds x_vqt_smoothed; any
+ * [n_frames][n_buckets] dB array works.  out: [n_frames][12].  Host and device-pointer forms. */
+int  pvqt_chroma(const pvqt_range *range, int device, const float *db, size_t n_frames, float *out);
+int  pvqt_chroma_device(const pvqt_range *range, int device, const float *d_db, size_t n_frames, float *d_out,
+                        void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

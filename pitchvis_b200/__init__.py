@@ -10,4 +10,5 @@ from .vqt import (  # noqa: F401
     VqtParameters, VqtRange, WindowExceedsNFft, WindowGroup, calc_db_device, fft_device, filter_bank_params,
     synchronize,
 )
-from .analysis import AnalysisParameters, AnalysisState, PeakDetectionParameters  # noqa: F401,E402
+from .analysis import AnalysisParameters, AnalysisState, PeakDetectionParameters, chroma  # noqa: F401,E402
+from .agc import AgcError, MonoAgc  # noqa: F401,E402

@@ -182,6 +182,17 @@ SIGNATURES = {
     "pvqt_analysis_preprocess_device": (C.c_int, [_VP, _VP, _SZ, _SZ, C.c_uint64, C.POINTER(PvqtAnalysisOutputs),
                                                   _VP]),
     "pvqt_analysis_synchronize": (C.c_int, [_VP]),
+    "pvqt_chroma": (C.c_int, [C.POINTER(PvqtRange), C.c_int, _FP, _SZ, _FP]),
+    "pvqt_chroma_device": (C.c_int, [C.POINTER(PvqtRange), C.c_int, _VP, _SZ, _VP, _VP]),
+    # include/pvqt_agc.h
+    "pvqt_agc_create": (C.c_int, [C.c_float, C.c_float, _SZ, C.c_int, C.POINTER(_VP)]),
+    "pvqt_agc_destroy": (None, [_VP]),
+    "pvqt_agc_n_streams": (_SZ, [_VP]),
+    "pvqt_agc_gains": (C.c_int, [_VP, _FP]),
+    "pvqt_agc_freeze_gain": (C.c_int, [_VP, C.c_int]),
+    "pvqt_agc_process": (C.c_int, [_VP, _FP, _SZ, _SZ, _SZ, C.c_float]),
+    "pvqt_agc_process_device": (C.c_int, [_VP, _VP, _SZ, _SZ, _SZ, C.c_float, _VP]),
+    "pvqt_agc_synchronize": (C.c_int, [_VP]),
 }
 
 _lib = None

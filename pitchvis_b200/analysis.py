@@ -141,3 +141,17 @@ class AnalysisState:
         out["peaks"] = set(int(i) for i in r["peak_indices"][0, 0, :n])
         out["peaks_continuous"] = r["peaks_continuous"][0, 0, :n]
         return out
+
+
+def chroma(db: np.ndarray, range: Optional[VqtRange] = None, device: int = 0) -> np.ndarray:
+    """Pitch-class energies of dB spectra (pitchvis_viewer/src/display_system/update.rs:1104-1131): [frames][12],
+    the per-class sums of 10^(dB/10) divided by their maximum."""
+    rng = range if range is not None else VqtRange()
+    x = np.ascontiguousarray(np.atleast_2d(db), np.float32)
+    if x.shape[1] != rng.n_buckets():
+        raise ValueError("db must be [frames][n_buckets]")
+    out = np.empty((x.shape[0], 12), np.float32)
+    r = PvqtRange(rng.min_freq, rng.octaves, rng.buckets_per_octave)
+    _check(_ffi.load().pvqt_chroma(C.byref(r), device, x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0],
+                                   out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out

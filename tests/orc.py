@@ -391,3 +391,47 @@ class OracleAnalysisState:
     @property
     def smoothed_tuning_grid_inaccuracy(self) -> float:
         return float(alib().orc_analysis_tuning_inaccuracy(self._h))
+
+
+# ---------------------------------------------------------------------------------------------------
+# AGC oracle (oracle/agc_oracle.c)
+# ---------------------------------------------------------------------------------------------------
+def agc_check(desired_output_rms: float, distortion_factor: float) -> int:
+    L = lib()
+    L.orc_agc_check.argtypes = [C.c_float, C.c_float]
+    return int(L.orc_agc_check(desired_output_rms, distortion_factor))
+
+
+def agc_process(samples: np.ndarray, desired_output_rms: float, distortion_factor: float, gain: float, frozen: bool):
+    """MonoAgc::process on one chunk; returns (processed samples, new gain)."""
+    L = lib()
+    L.orc_agc_process.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_float, C.POINTER(C.c_float), C.c_int]
+    L.orc_agc_process.restype = None
+    x = np.array(samples, np.float32, copy=True)
+    g = C.c_float(gain)
+    L.orc_agc_process(_fptr(x), x.shape[0], desired_output_rms, distortion_factor, C.byref(g), 1 if frozen else 0)
+    return x, float(g.value)
+
+
+def agc_process_chunks(samples: np.ndarray, chunk: int, desired_output_rms: float, distortion_factor: float,
+                       silence_threshold: float = 1e-6, gain: float = 1.0):
+    L = lib()
+    L.orc_agc_process_chunks.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float,
+                                         C.POINTER(C.c_float)]
+    L.orc_agc_process_chunks.restype = None
+    x = np.array(samples, np.float32, copy=True)
+    g = C.c_float(gain)
+    L.orc_agc_process_chunks(_fptr(x), x.shape[0], chunk, desired_output_rms, distortion_factor, silence_threshold,
+                             C.byref(g))
+    return x, float(g.value)
+
+
+def chroma(db: np.ndarray, min_freq: float = 55.0, buckets_per_octave: int = 84) -> np.ndarray:
+    """oracle/chroma_oracle.c: pitch-class energies of one dB frame (update.rs:1104-1131)."""
+    L = lib()
+    L.orc_chroma.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.c_uint32, C.POINTER(C.c_float)]
+    L.orc_chroma.restype = None
+    x = np.ascontiguousarray(db, np.float32)
+    out = np.empty(12, np.float32)
+    L.orc_chroma(_fptr(x), x.shape[0], min_freq, buckets_per_octave, _fptr(out))
+    return out
