@@ -330,6 +330,25 @@ def test_linearity_property_full_size(vqt):
         assert np.abs(one - db1[t]).max() <= TOL_DB
 
 
+def test_config3_slice_many_streams(vqt, oracle_default):
+    """BASELINE configs[2] in small: 96 independent 10 s streams (511 frames each, 49,056 frames: several launch
+    chunks of 16 streams, K-sdft chunk rows of different streams sharing CTAs).  Every stream equals its own
+    single-recording call bit for bit; one stream is checked against the oracle."""
+    base = [synth.polyphonic_chords(10.0, 22050.0, seed=100 + s) for s in range(6)]
+    n = base[0].shape[0]
+    assert n == 220500
+    streams = np.stack([base[s % 6] if s < 90 else np.roll(base[s % 6], 1000 * s) for s in range(96)])
+    out = vqt.calculate_vqt_streams_in_db(streams, HOP)
+    assert out.shape == (96, 511, 588) and np.all(np.isfinite(out)) and out.min() >= 0.0
+    singles = [vqt.calculate_vqt_batch_in_db(base[s], HOP) for s in range(6)]
+    for s in range(90):
+        np.testing.assert_array_equal(out[s], singles[s % 6])
+    for s in (90, 95):
+        np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+    ref = oracle_default.calculate_batch_db(base[3], HOP, mode=0)
+    assert np.abs(out[3] - ref).max() <= TOL_DB
+
+
 def test_hires_config(built_lib):
     # BASELINE configs[3]: more buckets per octave, an extra octave, 2x FFT window
     v = pv.Vqt(pv.VqtParameters.hires())
