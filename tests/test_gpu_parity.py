@@ -349,6 +349,28 @@ def test_config3_slice_many_streams(vqt, oracle_default):
     assert np.abs(out[3] - ref).max() <= TOL_DB
 
 
+def test_long_recording_crosses_launch_chunks(vqt, oracle_default):
+    """One recording longer than a launch chunk (8192 frames): the device entry cuts it into frame ranges, each with
+    its own K-sdft chunk rows; results must not depend on where the cuts fall."""
+    audio = synth.polyphonic_chords(175.0, 22050.0, seed=42)
+    n_frames = synth.frames_in(audio.shape[0], vqt.n_fft, HOP)
+    assert n_frames > 8192 + 1000
+    d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+    d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
+    d_audio.upload(audio)
+    pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out)
+    dev = d_out.download((n_frames, 588))
+    # the host entry cuts the same recording differently (copy/compute segments): same bits
+    np.testing.assert_array_equal(vqt.calculate_vqt_batch_in_db(audio, HOP), dev)
+    # frames around the cut against a call that starts elsewhere, and against the oracle
+    t0 = 8192 - 40
+    sub = vqt.calculate_vqt_batch_in_db(audio[t0 * HOP:], HOP, n_frames=80)
+    np.testing.assert_array_equal(sub, dev[t0:t0 + 80])
+    for t in (8190, 8191, 8192, 8193, n_frames - 1):
+        ref = oracle_default.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft], 0)
+        assert np.abs(dev[t] - ref).max() <= TOL_DB, t
+
+
 def test_hires_config(built_lib):
     # BASELINE configs[3]: more buckets per octave, an extra octave, 2x FFT window
     v = pv.Vqt(pv.VqtParameters.hires())
