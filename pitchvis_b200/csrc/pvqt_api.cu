@@ -144,6 +144,7 @@ struct pvqt {
     };
     std::vector<SdftPlan> sdft_plans;
     bool sdft_enabled = true;              // pvqt_set_sliding_dft
+    bool sdft_tensor_cores = true;         // mode 2 of pvqt_set_sliding_dft: partial sums on mma.sync (3xTF32)
 
     // scratch
     // One scratch set per launch lane: consecutive launch chains of a call alternate between kLanes internal
@@ -978,7 +979,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                     sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_r.ptr) + off);
                     off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                     prof_begin(v, 4, stream);
-                    cudaError_t e = launch_sdft_partial(sp, stream);
+                    cudaError_t e = launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
                     if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
                     prof_end(v, stream);
                     v->launches.fetch_add(1);
@@ -1737,12 +1738,13 @@ int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
     return PVQT_OK;
 }
 
-int pvqt_set_sliding_dft(pvqt *v, int enabled)
+int pvqt_set_sliding_dft(pvqt *v, int mode)
 {
     if (!v) return 0;
-    v->sdft_enabled = enabled != 0;
+    v->sdft_enabled = mode != 0;
+    v->sdft_tensor_cores = mode >= 2;
     if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
-    return v->sdft_enabled ? 1 : 0;
+    return v->sdft_enabled ? (v->sdft_tensor_cores ? 2 : 1) : 0;
 }
 
 int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches)

@@ -141,6 +141,185 @@ __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __g
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Partial sums on the tensor cores.  The inner level of the chunk twiddle, S_a[row][bin] = sum_b B[b][bin] x[row][16a+b],
+// is a dense real GEMM -- [rows x 16 samples] . [16 x (bins x {re, im})] -- the one block of this path that is a
+// real contraction: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, B = hi + lo; hi.hi + hi.lo +
+// lo.hi, products exact, f32 accumulate), which keeps the products at 2^-21 relative -- far inside the path's error
+// budget since the 16-sample sums are small against the chunk sums they feed.  The outer level, acc += A[a][bin] S_a
+// (one complex FMA per 16 samples instead of sixteen), stays on the FP32 pipe.  One warp owns 16 chunk rows x 16 bins
+// (4 n-tiles of 4 bins x {re, im}); the B fragments of its bins stay in registers for the whole kernel.
+// Fragment layouts (PTX ISA, mma.m16n8k8 .tf32): g = lane / 4, t = lane % 4;
+//   A (16x8, row):  a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+//   B (8x8, col):   b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   C (16x8):       c0 (g, 2t)  c1 (g, 2t+1)  c2 (g+8, 2t)  c3 (g+8, 2t+1)      -> (c0, c1) = (re, im) of bin t, row g
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaRowsPerCta = 16;
+constexpr int kMmaThreads = 128;   // 4 warps x 16 bins = 64 bins per CTA
+
+__device__ __forceinline__ uint32_t to_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kMmaThreads) sdft_partial_mma_kernel(const __grid_constant__ SdftParams P)
+{
+    extern __shared__ __align__(16) float4 sdft_smem[];
+    __shared__ const float *row_src[kMmaRowsPerCta];
+    __shared__ uint32_t row_valid[kMmaRowsPerCta];
+    float *xs = reinterpret_cast<float *>(sdft_smem);  // [16][row_stride]
+    const SdftGroup &G = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row_stride = G.hop_pad + 4;   // 4 or 20 modulo 32 words: the A-fragment loads of a warp hit 32 banks
+    const int bin0 = blockIdx.y * 64 + warp * 16;   // first of this warp's 16 bins (inside the consumed range)
+    const uint32_t total_rows = P.n_streams * P.rows_per_stream;
+    const uint32_t row0 = blockIdx.x * kMmaRowsPerCta;
+
+    pdl_launch_dependents();
+
+    if (tid < kMmaRowsPerCta) {
+        const uint32_t row = row0 + tid;
+        const float *src = nullptr;
+        uint32_t valid = 0;
+        if (row < total_rows) {
+            const uint32_t s = row / P.rows_per_stream;
+            const uint32_t c = P.first_frame + (row - s * P.rows_per_stream);
+            const uint64_t base = (uint64_t)c * G.hop + G.window_begin;
+            src = P.audio + (uint64_t)(P.first_stream + s) * P.stream_stride + base;
+            valid = base < P.valid_samples ? (uint32_t)min((uint64_t)G.hop, P.valid_samples - base) : 0u;
+        }
+        row_src[tid] = src;
+        row_valid[tid] = valid;
+    }
+    __syncthreads();
+    for (int r = 0; r < kMmaRowsPerCta; ++r) {
+        const float *src = row_src[r];
+        const uint32_t valid = row_valid[r];
+        float *dst = xs + r * row_stride;
+        for (int j = tid; j < G.hop_pad; j += kMmaThreads) {
+            const bool ok = (uint32_t)j < valid;
+            cp_async4_zfill(dst + j, ok ? src + j : P.audio, ok ? 4u : 0u);
+        }
+    }
+
+    // B fragments of this warp's bins, split hi / lo: n-tile q covers bins bin0 + 4q .. + 3; column n = g is
+    // (bin bin0 + 4q + g / 2, re if g even else im); k-step h covers samples b = 8h + k
+    uint32_t bhi[4][2][2], blo[4][2][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int bin = bin0 + 4 * q + (g >> 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int b = 8 * h + t + 4 * i;
+                float v = 0.f;
+                if (bin < G.nk) {
+                    const float2 w = __ldg(G.tw_b + b * G.nk + bin);
+                    v = (g & 1) ? w.y : w.x;
+                }
+                const uint32_t hi = to_tf32(v);
+                bhi[q][h][i] = hi;
+                blo[q][h][i] = to_tf32(v - __uint_as_float(hi));
+            }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    float2 acc[4][2];   // [n-tile][row g / row g+8]: complex running sum of bin bin0 + 4q + t
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = make_float2(0.f, 0.f);
+    const int ra = G.rem >> 4, rb = G.rem & 15;
+    const float *xa = xs + g * row_stride + t;
+    const float *xb = xs + (g + 8) * row_stride + t;
+
+    // S[q] = (16 samples of block a, samples b >= limit zeroed) . B, three TF32 products, small terms first
+    auto block_sums = [&](int a, int limit, float (&S)[4][4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) S[q][i] = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = 16 * a + 8 * h;
+            float x[4] = {xa[b], xb[b], xa[b + 4], xb[b + 4]};
+            if (8 * h + t >= limit) x[0] = x[1] = 0.f;
+            if (8 * h + t + 4 >= limit) x[2] = x[3] = 0.f;
+            uint32_t ahi[4], alo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ahi[i] = to_tf32(x[i]);
+                alo[i] = to_tf32(x[i] - __uint_as_float(ahi[i]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mma_tf32(S[q], alo, bhi[q][h][0], bhi[q][h][1]);
+                mma_tf32(S[q], ahi, blo[q][h][0], blo[q][h][1]);
+                mma_tf32(S[q], ahi, bhi[q][h][0], bhi[q][h][1]);
+            }
+        }
+    };
+    // acc += A * S for the thread's two rows of n-tile q
+    auto mac = [](float2 acc_in, float2 A, float sr, float si) {
+        float2 r = __ffma2_rn(make_float2(A.x, A.x), make_float2(sr, si), acc_in);
+        return __ffma2_rn(make_float2(-A.y, A.y), make_float2(si, sr), r);
+    };
+
+    float2 An[4];   // outer twiddles of the next block: loaded one block ahead (an L2 round trip otherwise, per block)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int bin = bin0 + 4 * q + t;
+        An[q] = bin < G.nk ? __ldg(G.tw_a + bin) : make_float2(0.f, 0.f);
+    }
+    for (int a = 0; a < G.n_blocks; ++a) {
+        float2 A[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int bin = bin0 + 4 * q + t;
+            A[q] = An[q];
+            An[q] = (bin < G.nk && a + 1 < G.n_blocks) ? __ldg(G.tw_a + (a + 1) * G.nk + bin) : make_float2(0.f, 0.f);
+        }
+        float S[4][4];
+        if (a == ra && G.rem != 0) {
+            // the remainder ends in this block: R = running sum + A * (first rb samples of the block)
+            block_sums(a, rb, S);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int bin = bin0 + 4 * q + t;
+                const float2 r0 = mac(acc[q][0], A[q], S[q][0], S[q][1]), r1 = mac(acc[q][1], A[q], S[q][2], S[q][3]);
+                if (bin < G.nk) {
+                    if (row0 + g < total_rows) P.partial_r[(size_t)(row0 + g) * G.nk + bin] = r0;
+                    if (row0 + g + 8 < total_rows) P.partial_r[(size_t)(row0 + g + 8) * G.nk + bin] = r1;
+                }
+            }
+        }
+        block_sums(a, 16, S);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc[q][0] = mac(acc[q][0], A[q], S[q][0], S[q][1]);
+            acc[q][1] = mac(acc[q][1], A[q], S[q][2], S[q][3]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int bin = bin0 + 4 * q + t;
+        if (bin < G.nk) {
+            if (row0 + g < total_rows) P.partial_c[(size_t)(row0 + g) * G.nk + bin] = acc[q][0];
+            if (row0 + g + 8 < total_rows) P.partial_c[(size_t)(row0 + g + 8) * G.nk + bin] = acc[q][1];
+        }
+    }
+}
+
 // Stand-alone combine (one CTA per 8-frame tile); used when no K-fft launch follows the partial sums.
 __global__ void __launch_bounds__(kTileFrames * 64) sdft_combine_kernel(const __grid_constant__ SdftParams P)
 {
@@ -199,13 +378,22 @@ cudaError_t configure_sdft(int hop_pad)
     if (want > 200 * 1024 || dev < 0 || dev >= 64) return cudaErrorInvalidConfiguration;
     if (want <= configured[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(sdft_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sdft_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)kMmaRowsPerCta * (hop_pad + 4) * sizeof(float)));
     if (e == cudaSuccess) configured[dev] = want;
     return e;
 }
 
-cudaError_t launch_sdft_partial(const SdftParams &p, cudaStream_t stream)
+cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream)
 {
     const uint32_t rows = p.n_streams * p.rows_per_stream;
+    if (tensor_cores) {
+        const dim3 grid((rows + kMmaRowsPerCta - 1) / kMmaRowsPerCta, (p.g.nk + 63) / 64);
+        const size_t smem = (size_t)kMmaRowsPerCta * (p.g.hop_pad + 4) * sizeof(float);
+        sdft_partial_mma_kernel<<<grid, kMmaThreads, smem, stream>>>(p);
+        return cudaGetLastError();
+    }
     const dim3 grid((rows + kSdftRowsPerCta - 1) / kSdftRowsPerCta, (p.g.nk + 63) / 64);
     sdft_partial_kernel<<<grid, kSdftThreads, sdft_smem_bytes(p.g.hop_pad), stream>>>(p);
     return cudaGetLastError();

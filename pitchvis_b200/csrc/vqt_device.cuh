@@ -242,7 +242,7 @@ constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
 constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
 
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream);
-cudaError_t launch_sdft_partial(const SdftParams &p, cudaStream_t stream);
+cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream);
 cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream);
 cudaError_t configure_sdft(int hop_pad);
 cudaError_t configure_sdft_combine(int q, int nk);

@@ -244,9 +244,11 @@ class Vqt:
                 "fft_block_threads", "spec_stride", "sdft_plans")
         return dict(zip(keys, [int(x) for x in out]))
 
-    def set_sliding_dft(self, enabled: bool) -> bool:
-        """Tuning / test switch: False keeps every window group on the per-frame FFT path in batched calls."""
-        return bool(self._lib.pvqt_set_sliding_dft(self._h, 1 if enabled else 0))
+    def set_sliding_dft(self, mode) -> int:
+        """Tuning / test switch: 0 / False keeps every window group on the per-frame FFT path in batched calls,
+        1 = K-sdft with the partial sums on the FP32 pipe, 2 / True (default) = on the tensor cores."""
+        m = 2 if mode is True else (0 if mode is False else int(mode))
+        return int(self._lib.pvqt_set_sliding_dft(self._h, m))
 
     # ---- per-frame entry point (vqt.rs:866) ----------------------------------------------
     def calculate_vqt_instant_in_db(self, x) -> np.ndarray:

@@ -248,6 +248,13 @@ def test_sliding_dft_path(vqt, oracle_default, chords):
         ref = oracle_default.calculate_batch_db(streams[s], HOP, mode=0)
         assert np.abs(got[s] - ref).max() <= TOL_DB
         np.testing.assert_array_equal(got[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
+    # the partial sums on the FP32 pipe (mode 1) and on the tensor cores (mode 2, 3xTF32) agree far inside the tolerance
+    try:
+        assert vqt.set_sliding_dft(1) == 1
+        ffma = vqt.calculate_vqt_streams_in_db(streams, HOP)
+    finally:
+        assert vqt.set_sliding_dft(2) == 2
+    assert np.abs(ffma - got).max() <= 2e-4
     # a hop that is not a multiple of 16 and leaves a remainder that ends inside a 16-sample block
     hop = 333
     nf = 60
