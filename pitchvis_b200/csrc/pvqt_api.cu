@@ -1006,8 +1006,12 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             }
             fp.n_groups = kept;
             fp.n_sdft = 0;
+            // the combine step runs inside K-spmm-db (one-CTA form); K-fft's last CTAs take it over for the other
+            // SpMM forms and for the spectra test hook
+            const bool combine_in_spmm = v->fused_ok && !v->cluster_ok && !d_spec_out;
             if (kept > 0) {
-                for (const auto &sp : sd) fp.sdft[fp.n_sdft++] = sp;
+                if (!combine_in_spmm)
+                    for (const auto &sp : sd) fp.sdft[fp.n_sdft++] = sp;
                 fp.combine_group = kept - 1;  // the last group: its CTAs start when the partial sums are long complete
                 prof_begin(v, 0, stream);
                 cudaError_t e = launch_fft(fp, ctas, v->fft_block_threads, stream);
@@ -1017,7 +1021,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             }
 
             // ---- K-sdft combine: run by K-fft's last CTAs; its own launch only when no FFT group is left ----
-            if (kept == 0)
+            if (kept == 0 && !combine_in_spmm)
                 for (const auto &sp : sd) {
                     prof_begin(v, 5, stream);
                     cudaError_t e = launch_sdft_combine(sp, stream);
@@ -1050,6 +1054,8 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 up.spec = spec;
                 up.out_db = d_out + f0 * nb;
                 up.power = d_power ? d_power + f0 * nb : nullptr;
+                up.n_sdft = 0;
+                for (const auto &sp : sd) up.sdft[up.n_sdft++] = sp;
                 prof_begin(v, 3, stream);
                 e = launch_spmm_db_fused(up, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_fused_kernel");

@@ -186,6 +186,8 @@ struct FusedParams {
     float   *out_db;           // [n_frames][n_buckets]
     float   *power;            // optional [n_frames][n_buckets]
     float    ref_db;
+    int32_t  n_sdft;           // K-sdft groups whose combine step this kernel runs while it stages the tile
+    SdftParams sdft[kMaxSdft];
 };
 
 // K-spmm-db, cluster form ("coefficient-stationary"): a thread-block cluster of CS CTAs splits the kernel

@@ -544,7 +544,34 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
         for (int i = threadIdx.x; i < n16; i += blockDim.x) {
             const int c = i >> 2, p = i & 3;     // physical chunk p of column c
             const int q = p ^ ((c >> 1) & 3);    // logical chunk: 0,1 = Re frames 0-3, 4-7; 2,3 = Im
-            cp_async16(fused_smem + q * PLANE + c, src + i);
+            bool from_sdft = false;              // columns the combine below produces are not copied
+            for (int gi = 0; gi < P.n_sdft; ++gi)
+                from_sdft |= c >= P.sdft[gi].g.spec_offset && c < P.sdft[gi].g.spec_offset + P.sdft[gi].g.nk;
+            if (!from_sdft) cp_async16(fused_smem + q * PLANE + c, src + i);
+        }
+    }
+    // K-sdft combine for this tile, straight into the planes (the columns of those groups are not in `spec`):
+    // X_t[k] = sum_i phase[i][k] C[row(t) + i][k] (+ remainder), every CTA its own 8 frames, while the cp.async
+    // copies above are in flight.  As an epilogue of K-fft's last CTAs the same step cost 8 us of that kernel's tail.
+    for (int gi = 0; gi < P.n_sdft; ++gi) {
+        const SdftParams &D = P.sdft[gi];
+        const SdftGroup &G = D.g;
+        const uint32_t lf0 = tile * kTileFrames, total = D.n_streams * D.frames;
+        const int items = kTileFrames * G.nk;
+        for (int item = threadIdx.x; item < items; item += blockDim.x) {
+            const int fi = item / G.nk, k = item - fi * G.nk;
+            const uint32_t lf = lf0 + fi;
+            float2 x = make_float2(0.f, 0.f);
+            if (lf < total) {
+                const uint32_t st = lf / D.frames, t = lf - st * D.frames;
+                const size_t row = (size_t)st * D.rows_per_stream + t;
+                x = sdft_dot(D.partial_c + row * G.nk + k, G.phase + k, G.q, G.nk);
+                if (G.rem != 0) x = __fadd2_rn(x, cmul(D.partial_r[(row + G.q) * G.nk + k], __ldg(G.phase + G.q * G.nk + k)));
+            }
+            float *re_plane = reinterpret_cast<float *>(fused_smem + (fi >> 2) * PLANE + G.spec_offset + k);
+            float *im_plane = reinterpret_cast<float *>(fused_smem + (2 + (fi >> 2)) * PLANE + G.spec_offset + k);
+            re_plane[fi & 3] = x.x;
+            im_plane[fi & 3] = x.y;
         }
     }
     cp_async_wait_all();
