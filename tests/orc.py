@@ -68,14 +68,35 @@ ORC_OK, ORC_ABOVE_NYQUIST, ORC_WINDOW_EXCEEDS_NFFT, ORC_ASSERT, ORC_BAD_LENGTH =
 _lib = None
 
 
+def _cpu_tag() -> str:
+    """Identifies the host CPU the oracle was compiled for (-march=native): model name + feature flags."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            txt = fh.read()
+        model = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("model name")), "?")
+        flags = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("flags")), "")
+        return model + " | " + " ".join(sorted(flags.split()))
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
-    """Compile oracle/liboracle.so if missing or stale (gcc, a few seconds)."""
+    """Compile oracle/liboracle.so if missing, stale, or built with -march=native on a different CPU (the built
+    file travels to the GPU box, whose host CPU may differ).  gcc, a few seconds."""
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    tag_path = _LIB_PATH + ".cpu"
     stale = not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
-    if force or stale:
+    try:
+        with open(tag_path) as fh:
+            same_cpu = fh.read() == _cpu_tag()
+    except OSError:
+        same_cpu = False
+    if force or stale or not same_cpu:
         subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+        with open(tag_path, "w") as fh:
+            fh.write(_cpu_tag())
     return _LIB_PATH
 
 
