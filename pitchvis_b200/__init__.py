@@ -2,8 +2,7 @@
 
 The product is the C-ABI library `pitchvis_b200/lib/libpvqt.so` (include/pvqt.h), built from
 `pitchvis_b200/csrc/` by `python -m pitchvis_b200.build`.  This package is the thin Python host
-used by the tests and bench; the Rust shim (rust/) and the C++ header (pitchvis_b200/cpp/) bind
-the same ABI.  There is no CPU fallback.
+used by the tests and bench; the Rust shim crates (rust/) bind the same ABI.  There is no CPU fallback.
 """
 from .vqt import (  # noqa: F401
     AboveNyquist, CsMat, DeviceBuffer, HostKernel, MultiVqt, PvqtRuntimeError, Vqt, VqtError, VqtKernel,
