@@ -523,7 +523,7 @@ int build_fused_plan(pvqt *v)
     FusedParams &P = v->fused;
     std::memset(&P, 0, sizeof(P));
     cudaError_t e;
-    if ((e = upload(v, warps, &P.warps)) != cudaSuccess) return cuda_fail(e, "upload fused warps");
+    for (int w = 0; w < n_warps; ++w) P.warp[w] = warps[(size_t)w];
     if ((e = upload(v, lane_meta, &P.lane_meta)) != cudaSuccess) return cuda_fail(e, "upload fused lane_meta");
     if ((e = upload(v, lane_rows, &P.lane_rows)) != cudaSuccess) return cuda_fail(e, "upload fused lane_rows");
     if ((e = upload(v, values, &P.values)) != cudaSuccess) return cuda_fail(e, "upload fused values");

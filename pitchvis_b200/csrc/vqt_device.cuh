@@ -168,7 +168,8 @@ struct FusedWarp {
 };
 
 struct FusedParams {
-    const FusedWarp *warps;
+    FusedWarp warp[32];        // per-warp walk descriptors, by value: the coefficient prefetch at kernel start must not
+                               // wait for a (cold) global load
     const int4   *lane_meta;   // [warp][lane]: (col0, len, ncol0, nlen) in spectrum columns
     const int2   *lane_rows;   // [warp][lane]: (first output row, valid rows 0..rows_per_lane)
     const float4 *values;      // [copy][slot][row pair][lane]: (K[row0].re, K[row0].im, K[row1].re, K[row1].im)

@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     extern __shared__ __align__(16) float4 fused_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
-    const FusedWarp W = P.warps[warp];
+    const FusedWarp W = P.warp[warp];
     const int4 meta = __ldg(P.lane_meta + warp * 32 + lane);
     const int2 rows = __ldg(P.lane_rows + warp * 32 + lane);
     const float4 *values = P.values + (size_t)(tile % P.values_copies) * P.values_stride;
