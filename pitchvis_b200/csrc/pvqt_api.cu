@@ -838,6 +838,10 @@ int build_cluster_plan(pvqt *v)
     v->cluster_max_active = max_active;
     v->cluster_capable = true;
     v->cluster_ok = false;  // measured slower than the one-CTA-per-tile form on B200: opt-in, mode 2
+    if (const char *m = std::getenv("PVQT_SPMM_MODE")) {
+        v->cluster_ok = std::atoi(m) >= 2;
+        v->fused_ok = v->fused_capable && std::atoi(m) >= 1;
+    }
     return PVQT_OK;
 }
 
