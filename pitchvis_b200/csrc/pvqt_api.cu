@@ -145,6 +145,8 @@ struct pvqt {
     std::vector<SdftPlan> sdft_plans;
     bool sdft_enabled = true;              // pvqt_set_sliding_dft
     bool sdft_tensor_cores = true;         // mode 2 of pvqt_set_sliding_dft: partial sums on mma.sync (3xTF32)
+    int sdft_tc = 0;                       // 1: tcgen05 partial sums for the groups mode 2 selects; 2 (mode 3): also for
+                                           //    the larger groups only the tcgen05 form pays for (sdft_tc_worthwhile)
 
     // scratch
     // One scratch set per launch lane: consecutive launch chains of a call alternate between kLanes internal
@@ -560,6 +562,17 @@ bool sdft_worthwhile(size_t n_window, size_t nk, size_t hop, size_t frames_per_s
     return sdft < 0.7 * fft;
 }
 
+// With the inner GEMM on tcgen05 the partial sums cost little; what remains is the combine step (q + 1 complex MACs
+// per bin and frame, read from L2) against the FFT the group would otherwise run.
+bool sdft_tc_worthwhile(size_t n_window, size_t nk, size_t hop)
+{
+    if (hop < 16 || hop * 4 > n_window || nk == 0 || nk > 1024) return false;
+    const double q = (double)(n_window / hop);
+    const double sdft = 0.3 * (double)nk * (double)hop + 8.0 * nk * (q + 1);
+    const double fft = 1.6 * (double)n_window * std::log2((double)n_window);
+    return sdft < 0.7 * fft;
+}
+
 const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
 {
     *status = PVQT_OK;
@@ -572,7 +585,7 @@ const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         const size_t n = groups[gi].window_size();
         const size_t nk = v->n_cols[gi];
-        if (!sdft_worthwhile(n, nk, hop, 1u << 20)) continue;  // not even for a long stream
+        if (!sdft_worthwhile(n, nk, hop, 1u << 20) && !sdft_tc_worthwhile(n, nk, hop)) continue;  // not even for a long stream
         SdftGroup g{};
         g.window_begin = (int32_t)groups[gi].window_begin;
         g.n_window = (int32_t)n;
@@ -600,7 +613,8 @@ const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
         cudaError_t e;
         if ((e = upload(v, ta, &g.tw_a)) != cudaSuccess || (e = upload(v, tb, &g.tw_b)) != cudaSuccess ||
             (e = upload(v, ph, &g.phase)) != cudaSuccess || (e = configure_sdft(g.hop_pad)) != cudaSuccess ||
-            (e = configure_sdft_combine(g.q, g.nk)) != cudaSuccess) {
+            (e = configure_sdft_combine(g.q, g.nk)) != cudaSuccess ||
+            (sdft_tc_supported(g) && (e = configure_sdft_tc(g.n_blocks)) != cudaSuccess)) {
             *status = cuda_fail(e, "build K-sdft plan");
             return nullptr;
         }
@@ -908,7 +922,9 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
         if (plan)
             for (size_t i = 0; i < plan->groups.size(); ++i)
                 if ((int)sdft_groups.size() < kMaxSdft &&
-                    sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream))
+                    (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream) ||
+                     (v->sdft_tc >= 2 && frames_per_stream >= 256 && sdft_tc_supported(plan->groups[i]) &&
+                      sdft_tc_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop))))
                     sdft_groups.push_back((int)i);
     }
     auto on_sdft = [&](int gi) {
@@ -983,7 +999,8 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                     sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_r.ptr) + off);
                     off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                     prof_begin(v, 4, stream);
-                    cudaError_t e = launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
+                    cudaError_t e = (v->sdft_tc >= 1 && sdft_tc_supported(sp.g)) ? launch_sdft_partial_tc(sp, stream)
+                                                                                 : launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
                     if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
                     prof_end(v, stream);
                     v->launches.fetch_add(1);
@@ -1503,6 +1520,7 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
     if (const char *s = std::getenv("PVQT_HOST_LANES")) v->host_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
     if (const char *s = std::getenv("PVQT_SEGMENTS")) v->segments_per_batch = std::max(1, std::atoi(s));
     if (const char *s = std::getenv("PVQT_GRAPHS")) v->use_graphs = std::atoi(s) != 0;
+    if (const char *s = std::getenv("PVQT_SDFT_TC")) v->sdft_tc = std::max(0, std::min(std::atoi(s), 2));
     pvqt *raw = v.release();
     int rc = build_device_plan(raw);
     if (rc != PVQT_OK) {
@@ -1748,13 +1766,17 @@ int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
     return PVQT_OK;
 }
 
+void pvqt_debug_tc(unsigned long long *out) { pvqt_dev::sdft_tc_debug(out); }
+void pvqt_debug_tc_set(unsigned long long mode) { pvqt_dev::sdft_tc_debug_set(mode); }
+
 int pvqt_set_sliding_dft(pvqt *v, int mode)
 {
     if (!v) return 0;
     v->sdft_enabled = mode != 0;
     v->sdft_tensor_cores = mode >= 2;
+    v->sdft_tc = mode >= 3 ? 2 : 0;
     if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
-    return v->sdft_enabled ? (v->sdft_tensor_cores ? 2 : 1) : 0;
+    return v->sdft_enabled ? (v->sdft_tc ? 3 : v->sdft_tensor_cores ? 2 : 1) : 0;
 }
 
 int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches)

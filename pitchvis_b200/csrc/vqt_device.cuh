@@ -247,6 +247,11 @@ constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band 
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream);
 cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream);
 cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream);
+bool        sdft_tc_supported(const SdftGroup &g);          // sdft_tc_kernel.cu: the tcgen05 form of the partial sums
+cudaError_t configure_sdft_tc(int n_blocks);
+void        sdft_tc_debug(unsigned long long *out);
+void        sdft_tc_debug_set(unsigned long long mode);
+cudaError_t launch_sdft_partial_tc(const SdftParams &p, cudaStream_t stream);
 cudaError_t configure_sdft(int hop_pad);
 cudaError_t configure_sdft_combine(int q, int nk);
 size_t sdft_combine_smem_bytes(int q, int nk);
