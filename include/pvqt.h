@@ -206,8 +206,9 @@ int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n);
 /* Test / tuning switch: 0 keeps every window group on the per-frame FFT path; 1 and 2 (default) let groups whose
  * consumed bins are cheaper as sums of hop-sized partial DFTs shared between overlapping frames take the K-sdft
  * path in the batched entries (never in the per-frame / independent-frames entries), with the partial sums on the
- * FP32 pipe (1) or on the tensor cores (2: mma.sync TF32 with the 3xTF32 split).  All evaluate the same DFT; they
- * differ by f32 rounding only.  Returns the mode in effect. */
+ * FP32 pipe (1) or on the tensor cores (2: mma.sync TF32 with the 3xTF32 split; 3, opt-in: tcgen05.mma with the
+ * accumulators in TMEM, for hops whose window remainder is a multiple of 16 samples, else as 2).  All evaluate the
+ * same DFT; they differ by f32 rounding only.  Returns the mode in effect. */
 int pvqt_set_sliding_dft(pvqt *v, int mode);
 
 /* ---- sharding (frame ranges / streams, no collective) ---------- */

@@ -141,12 +141,13 @@ struct pvqt {
         size_t hop = 0;
         std::vector<int> group_index;      // window groups this hop has tables for
         std::vector<SdftGroup> groups;     // device tables
+        std::vector<SdftTcPlan> tc;        // per group: plan of the tcgen05 form (n_groups = 0: not available)
     };
     std::vector<SdftPlan> sdft_plans;
     bool sdft_enabled = true;              // pvqt_set_sliding_dft
     bool sdft_tensor_cores = true;         // mode 2 of pvqt_set_sliding_dft: partial sums on mma.sync (3xTF32)
-    int sdft_tc = 0;                       // 1: tcgen05 partial sums for the groups mode 2 selects; 2 (mode 3): also for
-                                           //    the larger groups only the tcgen05 form pays for (sdft_tc_worthwhile)
+    int sdft_tc = 0;                       // 1 (mode 3): tcgen05 partial sums for the groups mode 2 selects; 2 (PVQT_SDFT_TC=2,
+                                           //    experiment): also the larger groups sdft_tc_worthwhile() accepts
 
     // scratch
     // One scratch set per launch lane: consecutive launch chains of a call alternate between kLanes internal
@@ -613,11 +614,28 @@ const pvqt::SdftPlan *sdft_plan_for(pvqt *v, size_t hop, int *status)
         cudaError_t e;
         if ((e = upload(v, ta, &g.tw_a)) != cudaSuccess || (e = upload(v, tb, &g.tw_b)) != cudaSuccess ||
             (e = upload(v, ph, &g.phase)) != cudaSuccess || (e = configure_sdft(g.hop_pad)) != cudaSuccess ||
-            (e = configure_sdft_combine(g.q, g.nk)) != cudaSuccess ||
-            (sdft_tc_supported(g) && (e = configure_sdft_tc(g.n_blocks)) != cudaSuccess)) {
+            (e = configure_sdft_combine(g.q, g.nk)) != cudaSuccess) {
             *status = cuda_fail(e, "build K-sdft plan");
             return nullptr;
         }
+        SdftTcPlan tc{};
+        if (sdft_tc_supported(g)) {
+            int group16 = 1;
+            if (const char *s = std::getenv("PVQT_TC_GROUP")) group16 = std::max(1, std::min(std::atoi(s) / 16, 4));
+            sdft_tc_make_plan(g, group16, &tc);
+            std::vector<float2> tgb((size_t)16 * group16 * nk), tgg((size_t)tc.n_groups * nk);
+            for (size_t k = 0; k < nk; ++k) {
+                const uint64_t ka = g.k_lo + k;
+                for (int b = 0; b < 16 * group16; ++b) tgb[(size_t)b * nk + k] = tw(ka, b);
+                for (int i = 0; i < tc.n_groups; ++i) tgg[(size_t)i * nk + k] = tw(ka, 16ull * tc.start16[i]);
+            }
+            if ((e = upload(v, tgb, &tc.tw_b)) != cudaSuccess || (e = upload(v, tgg, &tc.tw_g)) != cudaSuccess ||
+                (e = configure_sdft_tc(tc)) != cudaSuccess) {
+                *status = cuda_fail(e, "build K-sdft tcgen05 plan");
+                return nullptr;
+            }
+        }
+        plan.tc.push_back(tc);
         plan.group_index.push_back((int)gi);
         plan.groups.push_back(g);
     }
@@ -923,7 +941,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             for (size_t i = 0; i < plan->groups.size(); ++i)
                 if ((int)sdft_groups.size() < kMaxSdft &&
                     (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream) ||
-                     (v->sdft_tc >= 2 && frames_per_stream >= 256 && sdft_tc_supported(plan->groups[i]) &&
+                     (v->sdft_tc >= 2 && frames_per_stream >= 256 && plan->tc[i].n_groups > 0 &&
                       sdft_tc_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop))))
                     sdft_groups.push_back((int)i);
     }
@@ -973,7 +991,9 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
 
             // ---- K-sdft partial sums ----
             std::vector<SdftParams> sd;
+            std::vector<int> sd_plan;   // index into plan->groups / plan->tc
             for (int i : sdft_groups) {
+                sd_plan.push_back(i);
                 SdftParams sp{};
                 sp.g = plan->groups[(size_t)i];
                 sp.audio = d_audio;
@@ -994,12 +1014,14 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 if (L.sdft_c.reserve(need) != cudaSuccess || L.sdft_r.reserve(need) != cudaSuccess)
                     return cuda_fail(cudaGetLastError(), "allocate K-sdft scratch");
                 size_t off = 0;
-                for (auto &sp : sd) {
+                for (size_t si = 0; si < sd.size(); ++si) {
+                    SdftParams &sp = sd[si];
+                    const SdftTcPlan &tc = plan->tc[(size_t)sd_plan[si]];
                     sp.partial_c = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_c.ptr) + off);
                     sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_r.ptr) + off);
                     off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
                     prof_begin(v, 4, stream);
-                    cudaError_t e = (v->sdft_tc >= 1 && sdft_tc_supported(sp.g)) ? launch_sdft_partial_tc(sp, stream)
+                    cudaError_t e = (v->sdft_tc >= 1 && tc.n_groups > 0) ? launch_sdft_partial_tc(sp, tc, stream)
                                                                                  : launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
                     if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
                     prof_end(v, stream);
@@ -1766,15 +1788,13 @@ int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
     return PVQT_OK;
 }
 
-void pvqt_debug_tc(unsigned long long *out) { pvqt_dev::sdft_tc_debug(out); }
-void pvqt_debug_tc_set(unsigned long long mode) { pvqt_dev::sdft_tc_debug_set(mode); }
 
 int pvqt_set_sliding_dft(pvqt *v, int mode)
 {
     if (!v) return 0;
     v->sdft_enabled = mode != 0;
     v->sdft_tensor_cores = mode >= 2;
-    v->sdft_tc = mode >= 3 ? 2 : 0;
+    v->sdft_tc = mode >= 3 ? 1 : 0;
     if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
     return v->sdft_enabled ? (v->sdft_tc ? 3 : v->sdft_tensor_cores ? 2 : 1) : 0;
 }

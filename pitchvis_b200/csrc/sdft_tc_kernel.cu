@@ -1,41 +1,32 @@
 // sdft_tc_kernel.cu -- K-sdft partial sums on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
 // Same result as sdft_partial_mma_kernel (sdft_kernels.cu): C[row][k] and R[row][k] of one window group, the chunk
-// twiddle split in two levels e^{-2 pi i k (16 a + b) / N} = A[a][k] B[b][k].  The inner level is a dense real GEMM
-//   S_a[row][col] = sum_{b < 16} x[row][16 a + b] * Bt[col][b],      col = 2 * bin + {0: re, 1: im}
-// issued here as tcgen05.mma.kind::tf32, M = 128 chunk rows x N = 2 * BINS columns x K = 8 per instruction, with the
-// 3xTF32 split (x = hi + lo, B = hi + lo; lo.hi + hi.lo + hi.hi, f32 accumulate in TMEM): six MMAs per 16-sample
-// block.  The outer level, acc += A[a][k] S_a (one complex FMA per bin and block), stays on the FP32 pipe with the
-// running sums in registers: one thread per (row, 32 bins), read back from TMEM with tcgen05.ld.32x32b.
+// twiddle split in two levels: the chunk is cut into accumulation groups of up to G samples (G = 16, 32 or 64; a
+// cut at `rem`), e^{-2 pi i k (s_g + b) / N} = A[g][k] B[b][k] for sample b of the group starting at s_g.  The inner
+// level is a dense real GEMM
+//   S_g[row][col] = sum_{b < len_g} x[row][s_g + b] * Bt[col][b]
+// issued as tcgen05.mma.kind::tf32, M = 128 chunk rows x N = 128 columns x K = 8 per instruction, with the 3xTF32
+// split (x = hi + lo, B = hi + lo; lo.hi + hi.lo + hi.hi, f32 accumulate in TMEM): six MMAs per 16 samples.  The outer
+// level, acc += A[g][k] S_g (one complex FMA per bin and group), stays on the FP32 pipe with the running sums in
+// registers: one thread per (row, 32 bins), S_g read back from TMEM with tcgen05.ld.32x32b.  Columns come in
+// bin pairs, (re b0, re b1, im b0, im b1), so that the packed FFMA2s of the outer level need no register swaps.
 //
-// Shared-memory operands use the no-swizzle K-major canonical layout (8 rows x 16 bytes core matrices):
-//   element (row r, sample b) of a 16-sample block at float index ((b / 4) * 128 + r) * 4 + b % 4
-// so that one MMA's K = 8 slice is two 2048-byte planes (leading byte offset 2048, stride byte offset 128).
-// Pipeline per CTA (all warps in lock step, the tensor core asynchronous behind an mbarrier):
-//   cp.async raw block a+3 | split block a into hi / lo operand planes | one thread issues MMA(a) -> TMEM buffer a % 2
-//   | every thread folds S_{a-1} (TMEM buffer (a-1) % 2) into its running sums while MMA(a) runs.
+// Shared-memory operands: K-major, 64-byte swizzle -- one 16-sample block of a row is one 64-byte line.
+// Warp-specialised pipeline per CTA, every hand-over an mbarrier:
+//   loaders (thread = chunk row): aligned 16-byte loads, hi / lo split, fill a 4-slot operand ring
+//   one MMA thread: 6 MMAs per 16-sample block into one of 4 TMEM accumulators; tcgen05.commit frees the slot and,
+//                   after the group's last block, publishes the accumulator
+//   fold warps: tcgen05.ld, release the accumulator, acc += A[g] S_g
 // Selected for groups whose remainder `rem` is a multiple of 16 (R is then a snapshot of the running sum).
 #include "device_helpers.cuh"
 #include "vqt_device.cuh"
 
 namespace pvqt_dev {
-__device__ unsigned long long g_tc_debug[40];
 namespace {
 
 constexpr int kTcRows = 128;
-constexpr int kTcRawStride = 20;   // floats per row of a raw block: LDS.128 of 8 consecutive rows hit 32 banks
-constexpr int kTcRawRing = 4;
-constexpr int kTcRawBytes = kTcRows * kTcRawStride * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void cp_async4_zfill_tc(void *smem_dst, const void *gmem_src, unsigned src_bytes)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
@@ -50,14 +41,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
                  : "memory");
     return ok != 0;
 }
-// Bounded: a lost completion ends the kernel with wrong numbers (caught by the parity tests) instead of a hang.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-        if (mbar_try_wait(bar, parity)) break;
-    __syncwarp();
-}
-
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -123,6 +106,17 @@ __device__ __forceinline__ uint32_t tf32_rna(float x)
     return r;
 }
 
+// A 16-byte vector of a chunk row that reaches past the samples the stream holds: element-wise, zero filled.
+__device__ __noinline__ float4 ldv_tail(const float *src, int e0, int valid)
+{
+    float4 o;
+    o.x = (e0 >= 0 && e0 < valid) ? __ldg(src + e0) : 0.f;
+    o.y = (e0 + 1 >= 0 && e0 + 1 < valid) ? __ldg(src + e0 + 1) : 0.f;
+    o.z = (e0 + 2 >= 0 && e0 + 2 < valid) ? __ldg(src + e0 + 2) : 0.f;
+    o.w = (e0 + 3 >= 0 && e0 + 3 < valid) ? __ldg(src + e0 + 3) : 0.f;
+    return o;
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -130,36 +124,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 
 constexpr int kTcBins = 64;                 // bins per CTA tile: MMA N = 128 accumulator columns
 constexpr int kTcCols = 2 * kTcBins;
-constexpr int kTcSlots = 4;                 // A-operand ring (hi + lo planes per slot)
+constexpr int kTcSlots = 4;                 // A-operand ring (hi + lo tile per slot)
 constexpr int kTcAhead = 2;                 // blocks of audio a loader thread keeps in flight
 constexpr int kTcLoaderWarps = 4;           // thread = chunk row: loads, splits hi / lo, fills the ring
-constexpr int kTcEpiWarps = 8;              // thread = (chunk row, 32 bins): folds S_a into the running sums
+constexpr int kTcEpiWarps = 8;              // thread = (chunk row, 32 bins): folds S_g into the running sums
 constexpr int kTcThreads = (kTcLoaderWarps + 1 + kTcEpiWarps) * 32;
-constexpr int kTcPlaneA = 128 * 16;         // bytes of one k-quad plane of the A operand
-constexpr int kTcPlaneB = kTcCols * 16;
-constexpr int kTcOperandA = 4 * kTcPlaneA, kTcOperandB = 4 * kTcPlaneB;
+constexpr int kTcOperandA = 128 * 64;       // bytes of one operand tile: 128 rows x 16 samples
+constexpr int kTcOperandB = kTcCols * 64;
 constexpr int kTcBufs = 4;                  // TMEM accumulator buffers
 constexpr uint32_t kTcTmemCols = kTcBufs * kTcCols;
 
 struct TcBarriers {
     uint64_t full[kTcSlots];    // loaders -> MMA: slot holds block a            (one arrival per loader warp)
     uint64_t empty[kTcSlots];   // MMA -> loaders: the MMAs reading the slot are done (tcgen05.commit)
-    uint64_t tfull[kTcBufs];          // MMA -> epilogue: accumulator buffer holds S_a  (tcgen05.commit)
-    uint64_t tempty[kTcBufs];         // epilogue -> MMA: buffer read back              (one arrival per epilogue warp)
+    uint64_t tfull[kTcBufs];    // MMA -> fold: accumulator holds S_g             (tcgen05.commit)
+    uint64_t tempty[kTcBufs];   // fold -> MMA: accumulator read back             (one arrival per fold warp)
 };
 
-// Warp-specialised: warps 0-3 load + split, warp 4 issues the MMAs, warps 5-12 fold.  A wait that times out
-// raises `abort_flag`; every later wait then falls through, so a protocol bug ends in wrong numbers, not a hang.
-__global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __grid_constant__ SdftParams P)
+// A wait that times out raises `abort_flag`; every later wait then falls through, so a protocol bug ends in wrong
+// numbers (caught by the parity tests), not in a hang.
+__global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __grid_constant__ SdftParams P,
+                                                                         const __grid_constant__ SdftTcPlan T)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ __align__(8) TcBarriers bars;
     __shared__ uint32_t tmem_base_s;
     __shared__ volatile int abort_flag;
 
-    unsigned char *b_hi = tc_smem, *b_lo = b_hi + kTcOperandB;
-    unsigned char *a_op = b_lo + kTcOperandB;                                    // [slot][hi, lo]
-    float2 *tw_a_s = reinterpret_cast<float2 *>(a_op + kTcSlots * 2 * kTcOperandA);   // [n_blocks][kTcBins]
+    const int g16 = T.group16;                                                   // 16-sample blocks per full group
+    unsigned char *b_op = tc_smem;                                               // [sub-block][hi, lo]
+    unsigned char *a_op = b_op + g16 * 2 * kTcOperandB;                          // [slot][hi, lo]
+    float4 *tw_g_s = reinterpret_cast<float4 *>(a_op + kTcSlots * 2 * kTcOperandA);   // [group][bin pair]: (Ar0, Ar1, Ai0, Ai1)
 
     const SdftGroup &G = P.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -169,12 +164,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
     const int nb = G.n_blocks;
 
     pdl_launch_dependents();   // K-fft of the other groups may run beside this kernel
-    const long long t_start = clock64();
-    const bool dbg_cta = blockIdx.x == 1 && blockIdx.y == 0;
-    long long d_wait0 = 0, d_wait1 = 0, d_work = 0;
 
     auto wait = [&](uint64_t *bar, uint32_t parity) {
         if (abort_flag) return;
+#pragma unroll 1
         for (uint32_t spin = 0; spin < (1u << 16); ++spin)
             if (mbar_try_wait(bar, parity)) return;
         abort_flag = 1;
@@ -193,29 +186,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
         }
         fence_mbar_init();
     }
-    // B operand (inner twiddles, split hi / lo) and the outer twiddles of this CTA's bins
-    for (int idx = tid; idx < 16 * kTcCols; idx += kTcThreads) {
-        const int b = idx / kTcCols, n = idx - b * kTcCols, bin = bin0 + (n >> 1);
+    // B operand: inner twiddles of a full group, split hi / lo.  Column n of bin pair p = n / 4: re / im of bins
+    // 2p, 2p + 1 in the order (re0, re1, im0, im1).
+    for (int idx = tid; idx < 16 * g16 * kTcCols; idx += kTcThreads) {
+        const int b = idx / kTcCols, n = idx - b * kTcCols, bin = bin0 + 2 * (n >> 2) + (n & 1);
         float v = 0.f;
         if (bin < G.nk) {
-            const float2 w = __ldg(G.tw_b + b * G.nk + bin);
-            v = (n & 1) ? w.y : w.x;
+            const float2 w = __ldg(T.tw_b + b * G.nk + bin);
+            v = (n & 2) ? w.y : w.x;
         }
         const uint32_t hi = tf32_rna(v), lo = tf32_rna(v - __uint_as_float(hi));
-        const int off = sw64_offset(n, b >> 2) + (b & 3) * 4;
-        *reinterpret_cast<uint32_t *>(b_hi + off) = hi;
-        *reinterpret_cast<uint32_t *>(b_lo + off) = lo;
+        const int off = (b >> 4) * 2 * kTcOperandB + sw64_offset(n, (b >> 2) & 3) + (b & 3) * 4;
+        *reinterpret_cast<uint32_t *>(b_op + off) = hi;
+        *reinterpret_cast<uint32_t *>(b_op + off + kTcOperandB) = lo;
     }
-    for (int idx = tid; idx < nb * kTcBins; idx += kTcThreads) {
-        const int a = idx / kTcBins, j = idx - a * kTcBins;
-        tw_a_s[idx] = bin0 + j < G.nk ? __ldg(G.tw_a + a * G.nk + bin0 + j) : make_float2(0.f, 0.f);
+    for (int idx = tid; idx < T.n_groups * (kTcBins / 2); idx += kTcThreads) {
+        const int g = idx / (kTcBins / 2), p = idx - g * (kTcBins / 2), bin = bin0 + 2 * p;
+        const float2 w0 = bin < G.nk ? __ldg(T.tw_g + g * G.nk + bin) : make_float2(0.f, 0.f);
+        const float2 w1 = bin + 1 < G.nk ? __ldg(T.tw_g + g * G.nk + bin + 1) : make_float2(0.f, 0.f);
+        tw_g_s[idx] = make_float4(w0.x, w1.x, w0.y, w1.y);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const long long t_pro = clock64();
 
     if (warp < kTcLoaderWarps) {
         // ---------------- loaders: thread = chunk row ----------------
@@ -230,25 +225,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
             src = P.audio + (uint64_t)(P.first_stream + s) * P.stream_stride + base;
             valid = base < P.valid_samples ? (int)min((uint64_t)G.hop, P.valid_samples - base) : 0;
         }
-        // the row as aligned 16-byte vectors: vector v holds row elements 4 v - sh .. 4 v - sh + 3
+        // the row as aligned 16-byte vectors: vector v holds row elements 4 v - sh .. 4 v - sh + 3.  Elements before
+        // the row (v = 0, sh > 0) are read and dropped: they lie inside the same allocation.
         const int sh = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
         const float4 *p4 = reinterpret_cast<const float4 *>(src - sh);
         auto ldv = [&](int v) {
             const int e0 = 4 * v - sh;
-            if (e0 >= 0 && e0 + 3 < valid) return __ldg(p4 + v);
-            float4 o;
-            o.x = (e0 >= 0 && e0 < valid) ? __ldg(src + e0) : 0.f;
-            o.y = (e0 + 1 >= 0 && e0 + 1 < valid) ? __ldg(src + e0 + 1) : 0.f;
-            o.z = (e0 + 2 >= 0 && e0 + 2 < valid) ? __ldg(src + e0 + 2) : 0.f;
-            o.w = (e0 + 3 >= 0 && e0 + 3 < valid) ? __ldg(src + e0 + 3) : 0.f;
-            return o;
+            if (e0 + 3 < valid) return __ldg(p4 + v);
+            return ldv_tail(src, e0, valid);
         };
-        // register queue: the vectors of the next kTcAhead blocks are in flight
-        float4 carry = ldv(0), q[kTcAhead][4];
-#pragma unroll
-        for (int u = 0; u < kTcAhead; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) q[u][i] = u < nb ? ldv(4 * u + 1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         // the 4 row elements starting `sh` floats into the aligned pair (lo, hi): two levels of selects
         const bool s1 = sh & 1, s2 = sh & 2;
         auto shifted = [&](const float4 &lo, const float4 &hi) {
@@ -256,125 +241,123 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
                         a4 = s2 ? hi.z : hi.x;
             return make_float4(s1 ? a1 : a0, s1 ? a2 : a1, s1 ? a3 : a2, s1 ? a4 : a3);
         };
+        // register queue: the vectors of the next kTcAhead blocks are in flight
+        float4 carry = ldv(0), q[kTcAhead][4];
+#pragma unroll
+        for (int u = 0; u < kTcAhead; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[u][i] = u < nb ? ldv(4 * u + 1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int a0 = 0; a0 < nb; a0 += kTcAhead) {
 #pragma unroll
-        for (int u = 0; u < kTcAhead; ++u) {
-            const int a = a0 + u;
-            if (a >= nb) break;
-            float4 x[4];
-            x[0] = shifted(carry, q[u][0]);
+            for (int u = 0; u < kTcAhead; ++u) {
+                const int a = a0 + u;
+                if (a >= nb) break;
+                float4 x[4];
+                x[0] = shifted(carry, q[u][0]);
 #pragma unroll
-            for (int i = 1; i < 4; ++i) x[i] = shifted(q[u][i - 1], q[u][i]);
-            carry = q[u][3];
-            if (a + kTcAhead < nb) {
+                for (int i = 1; i < 4; ++i) x[i] = shifted(q[u][i - 1], q[u][i]);
+                carry = q[u][3];
+                if (a + kTcAhead < nb) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) q[u][i] = ldv(4 * (a + kTcAhead) + 1 + i);
+                    for (int i = 0; i < 4; ++i) q[u][i] = ldv(4 * (a + kTcAhead) + 1 + i);
+                }
+                const int slot = a % kTcSlots;
+                if (a >= kTcSlots) wait(&bars.empty[slot], (uint32_t)(a / kTcSlots - 1) & 1u);
+                unsigned char *hi_p = a_op + slot * 2 * kTcOperandA, *lo_p = hi_p + kTcOperandA;
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq) {
+                    uint4 h, l;
+                    h.x = tf32_rna(x[kq].x); l.x = tf32_rna(x[kq].x - __uint_as_float(h.x));
+                    h.y = tf32_rna(x[kq].y); l.y = tf32_rna(x[kq].y - __uint_as_float(h.y));
+                    h.z = tf32_rna(x[kq].z); l.z = tf32_rna(x[kq].z - __uint_as_float(h.z));
+                    h.w = tf32_rna(x[kq].w); l.w = tf32_rna(x[kq].w - __uint_as_float(h.w));
+                    *reinterpret_cast<uint4 *>(hi_p + sw64_offset(r, kq)) = h;
+                    *reinterpret_cast<uint4 *>(lo_p + sw64_offset(r, kq)) = l;
+                }
+                fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.full[slot]);
             }
-            const int slot = a % kTcSlots;
-            long long c0 = clock64();
-            if (a >= kTcSlots) wait(&bars.empty[slot], (uint32_t)(a / kTcSlots - 1) & 1u);
-            d_wait0 += clock64() - c0;
-            unsigned char *hi_p = a_op + slot * 2 * kTcOperandA, *lo_p = hi_p + kTcOperandA;
-#pragma unroll
-            for (int kq = 0; kq < 4; ++kq) {
-                uint4 h, l;
-                h.x = tf32_rna(x[kq].x); l.x = tf32_rna(x[kq].x - __uint_as_float(h.x));
-                h.y = tf32_rna(x[kq].y); l.y = tf32_rna(x[kq].y - __uint_as_float(h.y));
-                h.z = tf32_rna(x[kq].z); l.z = tf32_rna(x[kq].z - __uint_as_float(h.z));
-                h.w = tf32_rna(x[kq].w); l.w = tf32_rna(x[kq].w - __uint_as_float(h.w));
-                *reinterpret_cast<uint4 *>(hi_p + sw64_offset(r, kq)) = h;
-                *reinterpret_cast<uint4 *>(lo_p + sw64_offset(r, kq)) = l;
-            }
-            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.full[slot]);
         }
-        }
-        if (dbg_cta && tid == 0) { g_tc_debug[0] = d_wait0; g_tc_debug[1] = clock64() - t_pro; g_tc_debug[9] = t_pro - t_start; }
     } else if (warp == kTcLoaderWarps) {
         // ---------------- MMA issue: one thread ----------------
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc_tf32(kTcCols);
-            const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
-            for (int a = 0; a < nb; ++a) {
-                const int slot = a % kTcSlots, buf = a % kTcBufs;
-                long long c0 = clock64();
-                wait(&bars.full[slot], (uint32_t)(a / kTcSlots) & 1u);
-                d_wait0 += clock64() - c0; c0 = clock64();
-                if (a >= kTcBufs) wait(&bars.tempty[buf], (uint32_t)(a / kTcBufs - 1) & 1u);
-                d_wait1 += clock64() - c0; c0 = clock64();
-                tc_fence_after();
+            const uint32_t b0 = smem_u32(b_op);
+            for (int g = 0; g < T.n_groups; ++g) {
+                const int buf = g % kTcBufs, len = T.len16[g];
+                if (g >= kTcBufs) wait(&bars.tempty[buf], (uint32_t)(g / kTcBufs - 1) & 1u);
                 const uint32_t d = tmem_base + buf * kTcCols;
-                const uint32_t ah0 = smem_u32(a_op + slot * 2 * kTcOperandA), al0 = ah0 + kTcOperandA;
+                for (int j = 0; j < len; ++j) {
+                    const int a = T.start16[g] + j, slot = a % kTcSlots;
+                    wait(&bars.full[slot], (uint32_t)(a / kTcSlots) & 1u);
+                    tc_fence_after();
+                    const uint32_t ah0 = smem_u32(a_op + slot * 2 * kTcOperandA), al0 = ah0 + kTcOperandA;
+                    const uint32_t bh0 = b0 + j * 2 * kTcOperandB, bl0 = bh0 + kTcOperandB;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t ah = smem_desc(ah0 + h * 32), al = smem_desc(al0 + h * 32);   // K = 8 samples = 32 bytes
-                    const uint64_t bh = smem_desc(bh0 + h * 32), bl = smem_desc(bl0 + h * 32);
-                    mma_tf32_ss(d, al, bh, idesc, h);   // small terms first; h = 0 overwrites the buffer
-                    mma_tf32_ss(d, ah, bl, idesc, 1);
-                    mma_tf32_ss(d, ah, bh, idesc, 1);
+                    for (int h = 0; h < 2; ++h) {   // K = 8 samples = 32 bytes along the swizzled line
+                        const uint64_t ah = smem_desc(ah0 + h * 32), al = smem_desc(al0 + h * 32);
+                        const uint64_t bh = smem_desc(bh0 + h * 32), bl = smem_desc(bl0 + h * 32);
+                        mma_tf32_ss(d, al, bh, idesc, (j | h) != 0);   // small terms first; the first MMA overwrites
+                        mma_tf32_ss(d, ah, bl, idesc, 1);
+                        mma_tf32_ss(d, ah, bh, idesc, 1);
+                    }
+                    mma_commit(&bars.empty[slot]);
                 }
-                mma_commit(&bars.empty[slot]);
                 mma_commit(&bars.tfull[buf]);
-                d_work += clock64() - c0;
             }
-            if (dbg_cta) { g_tc_debug[2] = d_wait0; g_tc_debug[3] = d_wait1; g_tc_debug[4] = d_work; g_tc_debug[5] = clock64() - t_pro; }
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue: thread = (chunk row, 32 bins) ----------------
+        // ---------------- fold: thread = (chunk row, 32 bins = 16 bin pairs) ----------------
         const int e = warp - (kTcLoaderWarps + 1);
         const int quarter = warp & 3;                 // the TMEM lanes a warp may touch: 32 (warp % 4) .. + 31
-        const int my_bin = 32 * (e >> 2);             // first of the thread's 32 bins inside the CTA tile
+        const int my_pair = 16 * (e >> 2);            // first of the thread's bin pairs inside the CTA tile
         const uint32_t my_row = row0 + 32 * quarter + lane;
-        const uint32_t my_taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + 2 * my_bin;
-        const int ra = G.rem >> 4;
-        float2 acc[32];
-        const unsigned long long xmode = g_tc_debug[15];
+        const uint32_t my_taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + 4 * my_pair;
+        float2 re[16], im[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = make_float2(0.f, 0.f);
+        for (int j = 0; j < 16; ++j) re[j] = im[j] = make_float2(0.f, 0.f);
         auto store = [&](float2 *dst) {
             if (my_row < total_rows) {
-                float2 *o = dst + (size_t)my_row * G.nk + bin0 + my_bin;
+                float2 *o = dst + (size_t)my_row * G.nk + bin0 + 2 * my_pair;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (bin0 + my_bin + j < G.nk) o[j] = acc[j];
+                for (int j = 0; j < 16; ++j) {
+                    if (bin0 + 2 * (my_pair + j) < G.nk) o[2 * j] = make_float2(re[j].x, im[j].x);
+                    if (bin0 + 2 * (my_pair + j) + 1 < G.nk) o[2 * j + 1] = make_float2(re[j].y, im[j].y);
+                }
             }
         };
-        for (int a = 0; a < nb; ++a) {
-            const int buf = a % kTcBufs;
-            long long c0 = clock64();
-            wait(&bars.tfull[buf], (uint32_t)(a / kTcBufs) & 1u);
-            d_wait0 += clock64() - c0;
+        for (int g = 0; g < T.n_groups; ++g) {
+            const int buf = g % kTcBufs;
+            wait(&bars.tfull[buf], (uint32_t)(g / kTcBufs) & 1u);
             __syncwarp();
             tc_fence_after();
-            const float2 *A = tw_a_s + a * kTcBins + my_bin;
+            const float4 *A = tw_g_s + g * (kTcBins / 2) + my_pair;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float s[32];
-                if (!(xmode & 1)) tmem_ld32(my_taddr + buf * kTcCols + 32 * half, s);
-                else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) s[j] = (float)a;
-                }
+                tmem_ld32(my_taddr + buf * kTcCols + 32 * half, s);
                 if (half == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars.tempty[buf]);   // both halves are in registers: the buffer may be overwritten
+                    if (lane == 0) mbar_arrive(&bars.tempty[buf]);   // everything is in registers: the buffer may be overwritten
                 }
-                if (!(xmode & 2))
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 w = A[16 * half + j];
-                    float2 t = __ffma2_rn(make_float2(w.x, w.x), make_float2(s[2 * j], s[2 * j + 1]), acc[16 * half + j]);
-                    acc[16 * half + j] = __ffma2_rn(make_float2(-w.y, w.y), make_float2(s[2 * j + 1], s[2 * j]), t);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = A[8 * half + j];
+                    const float2 ar = make_float2(w.x, w.y), ai = make_float2(w.z, w.w);
+                    const float2 sr = make_float2(s[4 * j], s[4 * j + 1]), si = make_float2(s[4 * j + 2], s[4 * j + 3]);
+                    float2 &cr = re[8 * half + j], &ci = im[8 * half + j];
+                    cr = __ffma2_rn(ar, sr, cr);
+                    cr = __ffma2_rn(make_float2(-ai.x, -ai.y), si, cr);
+                    ci = __ffma2_rn(ar, si, ci);
+                    ci = __ffma2_rn(ai, sr, ci);
                 }
             }
-            if (a + 1 == ra && G.rem != 0) store(P.partial_r);   // rem = 16 ra: R is the running sum after ra blocks
+            if (g + 1 == T.r_groups) store(P.partial_r);   // the groups so far cover exactly the first `rem` samples
         }
-        const long long c1 = clock64();
         store(P.partial_c);
-        if (dbg_cta && e == 0 && lane == 0) { g_tc_debug[6] = d_wait0; g_tc_debug[7] = c1 - t_pro; g_tc_debug[8] = clock64() - c1; }
     }
 
     tc_fence_before();
@@ -382,25 +365,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
     if (warp == kTcLoaderWarps) tmem_dealloc(tmem_base, kTcTmemCols);
 }
 
-size_t tc_smem_bytes(int n_blocks)
+size_t tc_smem_bytes(int group16, int n_groups)
 {
-    return (size_t)2 * kTcOperandB + (size_t)kTcSlots * 2 * kTcOperandA + (size_t)n_blocks * kTcBins * sizeof(float2);
+    return (size_t)group16 * 2 * kTcOperandB + (size_t)kTcSlots * 2 * kTcOperandA + (size_t)n_groups * (kTcBins / 2) * sizeof(float4);
 }
 
 }  // namespace
 
 bool sdft_tc_supported(const SdftGroup &g)
 {
-    return g.rem % 16 == 0 && g.hop_pad == g.n_blocks * 16 && tc_smem_bytes(g.n_blocks) <= 200 * 1024;
+    return g.rem % 16 == 0 && g.hop_pad == g.n_blocks * 16 && g.n_blocks <= kTcMaxGroups;
 }
 
-cudaError_t configure_sdft_tc(int n_blocks)
+// Accumulation groups of up to 16 * group16 samples, cut at `rem`.
+void sdft_tc_make_plan(const SdftGroup &g, int group16, SdftTcPlan *t)
+{
+    *t = SdftTcPlan{};
+    t->group16 = group16;
+    const int r16 = g.rem / 16;
+    auto cut = [&](int a, int b) {
+        for (int s = a; s < b; s += group16) {
+            t->start16[t->n_groups] = (uint8_t)s;
+            t->len16[t->n_groups] = (uint8_t)std::min(group16, b - s);
+            ++t->n_groups;
+        }
+    };
+    cut(0, r16);
+    t->r_groups = t->n_groups;
+    cut(r16, g.n_blocks);
+}
+
+cudaError_t configure_sdft_tc(const SdftTcPlan &t)
 {
     static int configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const int want = (int)tc_smem_bytes(n_blocks);
+    const int want = (int)tc_smem_bytes(t.group16, t.n_groups);
     if (want > 200 * 1024 || dev < 0 || dev >= 64) return cudaErrorInvalidConfiguration;
     if (want <= configured[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(sdft_partial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want);
@@ -408,14 +409,11 @@ cudaError_t configure_sdft_tc(int n_blocks)
     return e;
 }
 
-void sdft_tc_debug_set(unsigned long long mode) { cudaMemcpyToSymbol(g_tc_debug, &mode, sizeof(mode), 15 * sizeof(unsigned long long)); }
-void sdft_tc_debug(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_tc_debug, sizeof(unsigned long long) * 40); }
-
-cudaError_t launch_sdft_partial_tc(const SdftParams &p, cudaStream_t stream)
+cudaError_t launch_sdft_partial_tc(const SdftParams &p, const SdftTcPlan &t, cudaStream_t stream)
 {
     const uint32_t rows = p.n_streams * p.rows_per_stream;
     const dim3 grid((rows + kTcRows - 1) / kTcRows, (p.g.nk + kTcBins - 1) / kTcBins);
-    sdft_partial_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(p.g.n_blocks), stream>>>(p);
+    sdft_partial_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(t.group16, t.n_groups), stream>>>(p, t);
     return cudaGetLastError();
 }
 

@@ -96,6 +96,17 @@ struct SdftParams {
     float       *spec;             // tiled planar layout; local frame = stream_local * frames + t
 };
 
+// Plan of the tcgen05 form of the partial sums (sdft_tc_kernel.cu): accumulation groups of 16-sample blocks.
+constexpr int kTcMaxGroups = 32;
+struct SdftTcPlan {
+    const float2 *tw_b;        // [16 * group16][nk]: e^{-2 pi i k b / N}, b inside a group
+    const float2 *tw_g;        // [n_groups][nk]:     e^{-2 pi i k s_g / N}, s_g the group's first sample
+    int32_t group16;           // 16-sample blocks per full group (1, 2 or 4)
+    int32_t n_groups;
+    int32_t r_groups;          // the first r_groups groups cover exactly the first `rem` samples (0: rem = 0)
+    uint8_t start16[kTcMaxGroups], len16[kTcMaxGroups];
+};
+
 struct FftParams {
     FftGroup    group[kMaxGroups];
     int32_t     n_groups;
@@ -248,10 +259,9 @@ cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cu
 cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream);
 cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream);
 bool        sdft_tc_supported(const SdftGroup &g);          // sdft_tc_kernel.cu: the tcgen05 form of the partial sums
-cudaError_t configure_sdft_tc(int n_blocks);
-void        sdft_tc_debug(unsigned long long *out);
-void        sdft_tc_debug_set(unsigned long long mode);
-cudaError_t launch_sdft_partial_tc(const SdftParams &p, cudaStream_t stream);
+void        sdft_tc_make_plan(const SdftGroup &g, int group16, SdftTcPlan *t);
+cudaError_t configure_sdft_tc(const SdftTcPlan &t);
+cudaError_t launch_sdft_partial_tc(const SdftParams &p, const SdftTcPlan &t, cudaStream_t stream);
 cudaError_t configure_sdft(int hop_pad);
 cudaError_t configure_sdft_combine(int q, int nk);
 size_t sdft_combine_smem_bytes(int q, int nk);

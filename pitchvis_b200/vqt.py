@@ -246,7 +246,8 @@ class Vqt:
 
     def set_sliding_dft(self, mode) -> int:
         """Tuning / test switch: 0 / False keeps every window group on the per-frame FFT path in batched calls,
-        1 = K-sdft with the partial sums on the FP32 pipe, 2 / True (default) = on the tensor cores."""
+        1 = K-sdft with the partial sums on the FP32 pipe, 2 / True (default) = on the tensor cores (mma.sync),
+        3 = on the tensor cores through tcgen05 / TMEM (opt-in; slower than 2 in round 1)."""
         m = 2 if mode is True else (0 if mode is False else int(mode))
         return int(self._lib.pvqt_set_sliding_dft(self._h, m))
 

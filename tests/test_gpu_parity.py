@@ -269,6 +269,47 @@ def test_sliding_dft_path(vqt, oracle_default, chords):
         vqt.set_sliding_dft(True)
 
 
+def test_sliding_dft_tcgen05(vqt, oracle_default, chords):
+    """Mode 3: the partial sums of K-sdft through tcgen05.mma / TMEM (sdft_tc_kernel.cu).  Same DFT as modes 1 and 2;
+    checked against numpy's f64 rfft, the oracle end to end (one long stream crossing many 128-row tiles, several
+    short streams sharing tiles, a stream shorter than the window remainder chain) and against mode 2."""
+    n_frames = 300
+    audio = chords[:vqt.n_fft + (n_frames - 1) * HOP]
+    n = vqt.n_fft + 39 * HOP
+    streams = np.stack([chords[o:o + n] for o in (0, 7001, 20000, 33333, 41234)])
+    mma = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    mma_s = vqt.calculate_vqt_streams_in_db(streams, HOP)
+    try:
+        assert vqt.set_sliding_dft(3) == 3
+        d_audio = pv.DeviceBuffer(vqt, audio.nbytes)
+        d_audio.upload(audio)
+        stride = vqt.spec_stride
+        n_tiles = (n_frames + 7) // 8
+        d_spec = pv.DeviceBuffer(vqt, n_tiles * stride * 8 * 8)
+        pv.fft_device(vqt, d_audio, 1, 0, HOP, n_frames, d_spec)
+        spec = _untile_spec(d_spec.download((n_tiles, stride, 16), np.float32), n_frames, stride)
+        wb, we = vqt.kernel().window_groups[0].window
+        first, n_cols, off = vqt.group_columns(0)
+        worst = 0.0
+        for t in (0, 1, 105, 106, 127, 128, 299):
+            full = np.fft.rfft(audio[t * HOP + wb:t * HOP + we].astype(np.float64))
+            got = spec[t, off:off + n_cols].astype(np.complex128)
+            worst = max(worst, np.abs(got - full[first:first + n_cols]).max() / np.abs(full).max())
+        assert worst <= 5e-7, worst
+        tc = vqt.calculate_vqt_batch_in_db(audio, HOP)
+        tc_s = vqt.calculate_vqt_streams_in_db(streams, HOP)
+        # a hop whose remainder is not a multiple of 16: mode 3 falls back to the mma.sync kernel
+        a2 = chords[1000:1000 + vqt.n_fft + 59 * 333]
+        tc_333 = vqt.calculate_vqt_batch_in_db(a2, 333)
+    finally:
+        assert vqt.set_sliding_dft(2) == 2
+    assert np.abs(tc - oracle_default.calculate_batch_db(audio, HOP, mode=0)).max() <= TOL_DB
+    for s in range(streams.shape[0]):
+        assert np.abs(tc_s[s] - oracle_default.calculate_batch_db(streams[s], HOP, mode=0)).max() <= TOL_DB
+    assert np.abs(tc - mma).max() <= 2e-4 and np.abs(tc_s - mma_s).max() <= 2e-4
+    np.testing.assert_array_equal(tc_333, vqt.calculate_vqt_batch_in_db(a2, 333))
+
+
 def test_edge_cases(vqt):
     n_fft = vqt.n_fft
     # silence -> all zeros (vqt.rs:944-951, second regime)
