@@ -109,6 +109,23 @@ int  pvqt_chroma(const pvqt_range *range, int device, const float *db, size_t n_
 int  pvqt_chroma_device(const pvqt_range *range, int device, const float *d_db, size_t n_frames, float *d_out,
                         void *cuda_stream);
 
+/* ---- spectrogram ring -------------------------------------------------------
+ * pitchvis_viewer/src/display_system/update.rs:930-1088, SpectrogramMode::VQT: every frame writes one RGBA8 row of
+ * width = n_buckets pixels into a ring image [height][n_buckets][4] -- row height-1-write_index --, clears the next
+ * row and advances write_index.  Alpha is the frame-normalised brightness of x_vqt_smoothed (update.rs:965-975,
+ * :989); RGB is a property of the bin alone (pitchvis_colors::calculate_color, an LCh round trip through the `lab`
+ * crate: a display concern) and is passed in as bytes already scaled as update.rs:986-988 does,
+ * bin_rgb[3 b + c] = (c * 255 * 1.2).clamp(0, 255) as u8.  n_frames frames at once: the image ends as if the
+ * reference had processed them one by one (the last min(n_frames, height-1) frames own a row each, the row after
+ * the last is cleared); *write_index is advanced by n_frames modulo height.  The Peaks mode of the same system
+ * (update.rs:997-1062) colours by fractional bin and stays on the host.  Host and device-pointer forms; the device
+ * form with height 1 is the caller's memset. */
+int  pvqt_spectrogram_vqt(int device, const float *smoothed, size_t n_frames, size_t n_buckets, const uint8_t *bin_rgb,
+                          uint8_t *image, size_t height, size_t *write_index);
+int  pvqt_spectrogram_vqt_device(int device, const float *d_smoothed, size_t n_frames, size_t n_buckets,
+                                 const uint8_t *d_bin_rgb, uint8_t *d_image, size_t height, size_t *write_index,
+                                 void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,5 +9,7 @@ from .vqt import (  # noqa: F401
     VqtParameters, VqtRange, WindowExceedsNFft, WindowGroup, calc_db_device, fft_device, filter_bank_params,
     synchronize,
 )
-from .analysis import AnalysisParameters, AnalysisState, PeakDetectionParameters, chroma  # noqa: F401,E402
+from .analysis import (  # noqa: F401,E402
+    AnalysisParameters, AnalysisState, PeakDetectionParameters, chroma, ml_input_windows, spectrogram_vqt,
+)
 from .agc import AgcError, MonoAgc  # noqa: F401,E402

@@ -184,6 +184,9 @@ SIGNATURES = {
     "pvqt_analysis_synchronize": (C.c_int, [_VP]),
     "pvqt_chroma": (C.c_int, [C.POINTER(PvqtRange), C.c_int, _FP, _SZ, _FP]),
     "pvqt_chroma_device": (C.c_int, [C.POINTER(PvqtRange), C.c_int, _VP, _SZ, _VP, _VP]),
+    "pvqt_spectrogram_vqt": (C.c_int, [C.c_int, _FP, _SZ, _SZ, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _SZ,
+                                       C.POINTER(C.c_size_t)]),
+    "pvqt_spectrogram_vqt_device": (C.c_int, [C.c_int, _VP, _SZ, _SZ, _VP, _VP, _SZ, C.POINTER(C.c_size_t), _VP]),
     # include/pvqt_agc.h
     "pvqt_agc_create": (C.c_int, [C.c_float, C.c_float, _SZ, C.c_int, C.POINTER(_VP)]),
     "pvqt_agc_destroy": (None, [_VP]),

@@ -155,3 +155,33 @@ def chroma(db: np.ndarray, range: Optional[VqtRange] = None, device: int = 0) ->
     _check(_ffi.load().pvqt_chroma(C.byref(r), device, x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0],
                                    out.ctypes.data_as(C.POINTER(C.c_float))))
     return out
+
+
+def spectrogram_vqt(smoothed: np.ndarray, bin_rgb: np.ndarray, image: np.ndarray, write_index: int, device: int = 0) -> int:
+    """The viewer's spectrogram ring in VQT mode (pitchvis_viewer/src/display_system/update.rs:930-1088) for all
+    frames of `smoothed` [frames][n_buckets] at once.  `image` is the RGBA8 ring [height][n_buckets][4], updated in
+    place; `bin_rgb` [n_buckets][3] are the per-bin colour bytes (pitchvis_colors::calculate_color, scaled as
+    update.rs:986-988).  Returns the new write index."""
+    x = np.ascontiguousarray(np.atleast_2d(smoothed), np.float32)
+    rgb = np.ascontiguousarray(bin_rgb, np.uint8)
+    if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 4 or not image.flags.c_contiguous:
+        raise ValueError("image must be a C-contiguous uint8 array [height][n_buckets][4]")
+    if image.shape[1] != x.shape[1] or rgb.shape != (x.shape[1], 3):
+        raise ValueError("smoothed [frames][n], bin_rgb [n][3] and image [height][n][4] must agree on n")
+    w = C.c_size_t(int(write_index))
+    u8 = C.POINTER(C.c_uint8)
+    _check(_ffi.load().pvqt_spectrogram_vqt(device, x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0], x.shape[1],
+                                            rgb.ctypes.data_as(u8), image.ctypes.data_as(u8), image.shape[0], C.byref(w)))
+    return int(w.value)
+
+
+def ml_input_windows(history: np.ndarray, t: int) -> np.ndarray:
+    """Model inputs as pitchvis_viewer/src/ml_system.rs:50-68 builds them: window i is the concatenation of frames
+    i .. i + t - 1 of `history` [frames][n] (the reference takes the last t frames per call).  A zero-copy view
+    [frames - t + 1][t * n] of the batched output: nothing to compute."""
+    h = np.ascontiguousarray(history, np.float32)
+    if h.ndim != 2 or t < 1 or h.shape[0] < t:
+        raise ValueError("history must be [frames][n] with frames >= t >= 1")
+    n = h.shape[1]
+    return np.lib.stride_tricks.as_strided(h, shape=(h.shape[0] - t + 1, t * n), strides=(h.strides[0], h.strides[1]),
+                                           writeable=False)

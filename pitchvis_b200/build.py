@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas"
               "--expt-relaxed-constexpr"]
 # the analysis epilogue mirrors un-contracted f32 expressions of the reference (see the file header)
 PER_FILE_FLAGS = {"analysis_kernels.cu": ["-fmad=false"], "agc_kernels.cu": ["-fmad=false"],
-                  "chroma_kernels.cu": ["-fmad=false"]}
+                  "chroma_kernels.cu": ["-fmad=false"], "spectrogram_kernels.cu": ["-fmad=false"]}
 # the kernel builder mirrors the reference's f32 op order: no FMA contraction on the host
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wextra"]
 

@@ -456,3 +456,20 @@ def chroma(db: np.ndarray, min_freq: float = 55.0, buckets_per_octave: int = 84)
     out = np.empty(12, np.float32)
     L.orc_chroma(_fptr(x), x.shape[0], min_freq, buckets_per_octave, _fptr(out))
     return out
+
+
+def spectrogram_vqt(smoothed: np.ndarray, bin_rgb: np.ndarray, image: np.ndarray, write_index: int) -> int:
+    """oracle/spectrogram_oracle.c: the spectrogram ring in VQT mode, one update_spectrogram_system call per frame
+    (update.rs:930-1088).  `image` [height][n][4] uint8 is updated in place; returns the new write index."""
+    L = lib()
+    u8 = C.POINTER(C.c_uint8)
+    L.orc_spectrogram_vqt_step.argtypes = [C.POINTER(C.c_float), C.c_size_t, u8, u8, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.orc_spectrogram_vqt_step.restype = None
+    x = np.ascontiguousarray(np.atleast_2d(smoothed), np.float32)
+    rgb = np.ascontiguousarray(bin_rgb, np.uint8)
+    assert image.dtype == np.uint8 and image.flags.c_contiguous and image.shape[1:] == (x.shape[1], 4)
+    w = C.c_size_t(write_index)
+    for t in range(x.shape[0]):
+        L.orc_spectrogram_vqt_step(_fptr(x[t]), x.shape[1], rgb.ctypes.data_as(u8), image.ctypes.data_as(u8), image.shape[0],
+                                   C.byref(w))
+    return int(w.value)
