@@ -1,7 +1,8 @@
 """numpy model of the tcgen05 K-sdft partial sums (sdft_tc_kernel.cu): 3xTF32 products, f32 accumulation in the
 tensor core with round-to-nearest ("rn") or truncation ("rz"), accumulation groups of G samples, outer rotation in
 f32, combine in f64.  Prints (max, median) of max_k |X - X_ref| / max_k |X_ref| over 200 frames of window group 1.
-On the B200 only G = 16 meets the 1e-3 dB bound: the hardware follows the "rz" rows.
+On the B200 G = 16 and 32 meet the parity bounds and G = 64 does not: the hardware follows the "rz" rows
+(DESIGN.md section 3).
 
     python scripts/tc_accumulation_model.py
 """
