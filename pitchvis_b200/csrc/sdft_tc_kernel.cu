@@ -141,8 +141,9 @@ struct TcBarriers {
     uint64_t tempty[kTcBufs];   // fold -> MMA: accumulator read back             (one arrival per fold warp)
 };
 
-// A wait that times out raises `abort_flag`; every later wait then falls through, so a protocol bug ends in wrong
-// numbers (caught by the parity tests), not in a hang.
+// Every wait is bounded (2^26 polls, seconds: far beyond any preemption of a healthy device).  A wait that does run
+// out raises `abort_flag` and every later wait falls through, so a protocol bug ends in wrong numbers -- which the
+// parity tests catch -- instead of a hung device.
 __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __grid_constant__ SdftParams P,
                                                                          const __grid_constant__ SdftTcPlan T)
 {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdft_partial_tc_kernel(const __
     auto wait = [&](uint64_t *bar, uint32_t parity) {
         if (abort_flag) return;
 #pragma unroll 1
-        for (uint32_t spin = 0; spin < (1u << 16); ++spin)
+        for (uint32_t spin = 0; spin < (1u << 26); ++spin)
             if (mbar_try_wait(bar, parity)) return;
         abort_flag = 1;
     };
