@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- VQT frames/sec on B200 (BASELINE.json metric), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload chords60|hires60]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload chords60|hires60|streams4096] [--streams S]
 
 A "step" is one pass of the hot path over one batch of synthetic audio.  At N=1 the workload is
 BASELINE.json configs[1]: 60 s of synthetic polyphonic audio (random chords), default VqtParameters,
 hop 368 -> 3507 frames.  With N ranks (torchrun, one rank per GPU) every rank transforms its own
 60 s recording (weak scaling, independent streams, no collective on the data path).
+`--workload streams4096` is BASELINE.json configs[2]: 4096 independent 10 s streams (511 frames each,
+2,093,056 frames in all), contiguous blocks of 4096/N streams per rank (strong scaling, total work fixed).
 
   value        frames/s, device-timed (CUDA events per step), audio already resident in HBM
   e2e          frames/s through the host-buffer C-ABI entry (pvqt_calc_batch_db): H2D + kernels + D2H
@@ -41,7 +44,13 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def workload(name: str, seed: int):
+def _stream(seed: int):
+    from pitchvis_b200 import synth
+    return synth.polyphonic_chords(10.0, 22050.0, seed=seed)
+
+
+def workload(name: str, seed: int, rank: int = 0, world: int = 1, n_streams_total: int = 4096):
+    """-> params, audio ([samples] or [streams][samples]), hop, n_streams (this rank), frames_per_stream"""
     from pitchvis_b200 import synth
     import pitchvis_b200 as pv
     if name == "chords60":
@@ -52,13 +61,31 @@ def workload(name: str, seed: int):
         params = pv.VqtParameters.hires()
         audio = synth.polyphonic_chords(60.0, params.sr, seed=seed)
         hop = synth.HOP_HIRES
+    elif name == "streams4096":
+        # stream s = the config-2 generator with seed s, 10 s each; rank r owns the
+        # contiguous block [r * S / world, (r + 1) * S / world)
+        params = pv.VqtParameters.default()
+        hop = synth.HOP_DEFAULT
+        s0, s1 = rank * n_streams_total // world, (rank + 1) * n_streams_total // world
+        import multiprocessing as mp
+        procs = max(1, min(host_threads(), 64))
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(procs) as pool:
+            rows = pool.map(_stream, range(s0, s1), chunksize=4)
+        audio = np.stack(rows)
+        log(f"generated {s1 - s0} streams in {time.perf_counter() - t0:.1f} s on {procs} processes")
     else:
         raise SystemExit(f"unknown workload {name}")
-    n_frames = synth.frames_in(audio.shape[0], params.n_fft, hop)
-    return params, audio, hop, n_frames
+    if audio.ndim == 1:
+        return params, audio, hop, 1, synth.frames_in(audio.shape[0], params.n_fft, hop)
+    return params, audio, hop, audio.shape[0], synth.frames_in(audio.shape[1], params.n_fft, hop)
 
 
-def workload_name(name: str, hop: int, n_frames: int) -> str:
+def workload_name(name: str, hop: int, n_frames: int, n_streams_total: int = 4096) -> str:
+    if name == "streams4096":
+        return (f"streams4096: {n_streams_total} independent 10 s synthetic streams (random chords, stream s = seed s), "
+                f"hop {hop}, {n_frames // max(1, n_streams_total)} frames/stream, {n_frames} frames/step over all "
+                f"GPUs, contiguous stream blocks per rank (BASELINE.json configs[2])")
     which = "BASELINE.json configs[1]" if name == "chords60" else "BASELINE.json configs[3]"
     return (f"{name}: 60 s synthetic polyphonic audio per GPU (random chords, seed = rank), hop {hop}, "
             f"{n_frames} frames/step/GPU ({which})")
@@ -66,7 +93,7 @@ def workload_name(name: str, hop: int, n_frames: int) -> str:
 
 def oracle_params(name: str):
     import orc
-    return orc.default_params() if name == "chords60" else orc.hires_params()
+    return orc.hires_params() if name == "hires60" else orc.default_params()
 
 
 class ClockSampler:
@@ -164,22 +191,38 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     import orc
-    params, audio, hop, n_frames = workload(args.workload, seed=0)
+    if args.workload == "streams4096":
+        # bounded sample of config 3: the first 16 streams of the 4096 (same frames-per-stream, same parameters)
+        params, audio, hop, n_streams, fps_ = workload(args.workload, seed=0, rank=0, world=args.streams // 16,
+                                                       n_streams_total=args.streams)
+    else:
+        params, audio, hop, n_streams, fps_ = workload(args.workload, seed=0)
+    n_frames = n_streams * fps_
+    rows = audio.reshape(n_streams, -1)
     v = orc.OracleVqt(oracle_params(args.workload))
     threads = host_threads()
+
+    def one_pass():
+        for r in rows:
+            v.calculate_batch_db(r, hop, fps_, mode=1, n_threads=threads)
+
     for _ in range(args.warmup):
-        v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+        one_pass()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
+        one_pass()
     dt = time.perf_counter() - t0
     fps = args.steps * n_frames / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "streams4096" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, hop, n_frames),
-                   "sample": "every step transforms all frames of the workload on the host cores (oracle f32 path)"},
+        "config": {"workload": workload_name(args.workload, hop, n_frames if args.workload != "streams4096"
+                                             else args.streams * fps_, args.streams),
+                   "sample": ("every step transforms all frames of the workload on the host cores (oracle f32 path)"
+                              if args.workload != "streams4096" else
+                              f"every step transforms the first {n_streams} streams ({n_frames} frames) of the workload")},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} passes over all {n_frames} frames of the workload, "
                                    "oracle f32 path (C port of vqt.rs:866-954; the Rust crate cannot be built here)"},
@@ -192,6 +235,9 @@ def cpu_baseline(args, audio, hop, n_frames):
     import orc
     v = orc.OracleVqt(oracle_params(args.workload))
     threads = host_threads()
+    if audio.ndim == 2:   # streams: the sample is the first stream (same parameters, same frames per stream)
+        audio = audio[0]
+        n_frames = n_frames // max(1, args.local_streams)
     v.calculate_batch_db(audio, hop, min(n_frames, 256), mode=1, n_threads=threads)  # warm caches / plans
     t0 = time.perf_counter()
     v.calculate_batch_db(audio, hop, n_frames, mode=1, n_threads=threads)
@@ -217,7 +263,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="chords60", choices=["chords60", "hires60"])
+    ap.add_argument("--workload", default="chords60", choices=["chords60", "hires60", "streams4096"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams4096 only: total streams over all ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed steps: write a 512 MiB buffer, or write it and read it back "
@@ -245,7 +292,14 @@ def main():
     from pitchvis_b200 import _ffi
     lib = _ffi.load()
 
-    params, audio, hop, n_frames = workload(args.workload, seed=rank)
+    params, audio, hop, n_streams, frames_per_stream = workload(args.workload, seed=rank, rank=rank, world=world,
+                                                                n_streams_total=args.streams)
+    n_frames = n_streams * frames_per_stream     # frames per step on this rank
+    args.local_streams = n_streams
+    stream_stride = audio.shape[1] if audio.ndim == 2 else 0
+    strong = args.workload == "streams4096"
+    if strong and args.steps == 50:
+        args.steps = 10                            # one step is ~50 ms of kernels here
     vqt = pv.Vqt(params, device=local_rank)
     nb = vqt.n_buckets
     h = vqt.handle
@@ -265,7 +319,7 @@ def main():
         chk(lib.pvqt_event_create(h, C.byref(e)))
 
     def step():
-        pv.calc_db_device(vqt, d_audio, 1, 0, hop, n_frames, d_out)
+        pv.calc_db_device(vqt, d_audio, n_streams, stream_stride, hop, frames_per_stream, d_out)
 
     def flush():
         if args.flush == "write":
@@ -321,14 +375,22 @@ def main():
     chk(lib.pvqt_host_alloc_pinned(n_frames * nb * 4, C.byref(pin_out)))
     C.memmove(pin_in, audio.ctypes.data, audio.nbytes)
     fp = C.POINTER(C.c_float)
-    e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
+    e2e_steps = max(3, min(args.steps, 20 if not strong else 3))
+
+    def e2e_call():
+        if audio.ndim == 1:
+            chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
+        else:
+            chk(lib.pvqt_calc_streams_db(h, C.cast(pin_in, fp), n_streams, stream_stride, audio.shape[1], hop,
+                                         frames_per_stream, C.cast(pin_out, fp)))
+
+    for _ in range(2 if not strong else 1):
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         # no L2 flush here: every step's input arrives from pinned host memory through H2D copies
-        chk(lib.pvqt_calc_batch_db(h, C.cast(pin_in, fp), audio.shape[0], hop, n_frames, C.cast(pin_out, fp)))
+        e2e_call()
     pv.synchronize(vqt)
     e2e_s = time.perf_counter() - t0
     result_checksum = float(np.ctypeslib.as_array(C.cast(pin_out, fp), shape=(n_frames * nb,)).sum())
@@ -343,6 +405,11 @@ def main():
         dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
 
     total_frames = world * n_frames
+    if strong and dist is not None:
+        import torch
+        t = torch.tensor([n_frames], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        total_frames = int(t[0])
     value = total_frames * args.steps / (dev_ms_max * 1e-3)
     e2e_value = total_frames * e2e_steps / e2e_s_max
 
@@ -367,9 +434,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload_name(args.workload, hop, n_frames),
+                "workload": workload_name(args.workload, hop, total_frames if strong else n_frames, args.streams),
                 "n_fft": params.n_fft, "n_buckets": nb, "hop": hop, "frames_per_step_per_gpu": n_frames,
                 "l2": f"flushed between timed steps ({flush_bytes >> 20} MiB memset"
                       + (" followed by a read sweep of the same buffer, so the flush leaves no dirty lines)"
@@ -378,7 +445,8 @@ def main():
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(audio.nbytes),
                     "d2h_bytes_per_step": int(n_frames * nb * 4), "steps": e2e_steps,
-                    "api": "pvqt_calc_batch_db (pinned host buffers in and out)", "checksum": result_checksum,
+                    "api": ("pvqt_calc_batch_db" if audio.ndim == 1 else "pvqt_calc_streams_db")
+                           + " (pinned host buffers in and out)", "checksum": result_checksum,
                     "host_cpus_near_gpu": near_cpus},
             "gpu_launches": int(launches),
             "plan": vqt.plan_info(),
