@@ -6,6 +6,7 @@ frame maximum; between -60 and -80 dB (clamped away by power_to_db) the bound is
 reference's own f32 FFT has -- see test_power_parity_above_minus_80_db.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -395,6 +396,39 @@ def test_config3_slice_many_streams(vqt, oracle_default):
         np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP))
     ref = oracle_default.calculate_batch_db(base[3], HOP, mode=0)
     assert np.abs(out[3] - ref).max() <= TOL_DB
+
+
+def _seeded_stream(seed):
+    return synth.polyphonic_chords(10.0, 22050.0, seed=seed)
+
+
+def test_config3_full_size_4096_streams(vqt, oracle_default):
+    """BASELINE configs[2] at full size: 4096 independent 10 s streams (stream s = the config-2 generator with seed s),
+    511 frames each, 2,093,056 frames, through the host-buffer entry pvqt_calc_streams_db.  Size-independent
+    properties: every sampled stream equals its own single-recording call bit for bit (no stream sees its
+    neighbours, wherever the launch chunks fall); sampled streams match the oracle within 1e-3 dB; every value is
+    finite and >= 0; a checksum of per-stream checksums over two different stream orders agrees exactly."""
+    import multiprocessing as mp
+    n_streams = 4096
+    procs = max(1, min(len(os.sched_getaffinity(0)), 64))
+    with mp.get_context("fork").Pool(procs) as pool:
+        streams = np.stack(pool.map(_seeded_stream, range(n_streams), chunksize=8))
+    assert streams.shape == (n_streams, 220500)
+    out = vqt.calculate_vqt_streams_in_db(streams, HOP)
+    assert out.shape == (n_streams, 511, 588)
+    assert np.isfinite(out).all() and out.min() >= 0.0
+    sample = [0, 1, 15, 16, 17, 2047, 2048, 4079, 4080, 4095]     # both sides of 16-stream launch chunks
+    for s in sample:
+        np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP), err_msg=f"stream {s}")
+    for s in (0, 2048, 4095):
+        ref = oracle_default.calculate_batch_db(streams[s], HOP, mode=0)
+        assert np.abs(out[s] - ref).max() <= TOL_DB, s
+    # order independence at full size: the second half first
+    sums = out.reshape(n_streams, -1).sum(axis=1, dtype=np.float64)
+    perm = np.concatenate([np.arange(2048, 4096), np.arange(0, 2048)])
+    out2 = vqt.calculate_vqt_streams_in_db(streams[perm], HOP, out=out)   # reuses the 4.9 GB buffer
+    sums2 = out2.reshape(n_streams, -1).sum(axis=1, dtype=np.float64)
+    np.testing.assert_array_equal(sums2, sums[perm])
 
 
 def test_long_recording_crosses_launch_chunks(vqt, oracle_default):
