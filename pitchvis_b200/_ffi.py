@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libpvqt.so")
+# PVQT_LIB: another build of the same library (kernel experiments: scripts/build_variant.sh); never a fallback
+LIB_PATH = os.environ.get("PVQT_LIB") or os.path.join(_PKG, "lib", "libpvqt.so")
 
 PROFILE_KINDS = 8  # PVQT_PROFILE_KINDS
 KERNEL_KIND_NAMES = ("fft_groups_kernel", "spmm_kernel", "power_to_db_kernel", "spmm_db_fused_kernel",

@@ -134,7 +134,9 @@ struct pvqt {
     std::vector<uint32_t> col_lo, n_cols, spec_off;
     size_t first_sample_used = 0;
     size_t last_sample_used = 0;        // one past
-    uint32_t chunk_frames = 8192;
+    uint32_t segment_cap = 16384;       // frames per copy/compute segment of the host-buffer entries (PVQT_SEGMENT_FRAMES)
+    uint32_t chunk_frames = 131072;     // frames per launch (PVQT_CHUNK_FRAMES): measured 42.4 M frames/s at 8192, 46.7 M at
+                                        // 131072 on 1024 streams x 511 frames (scripts/chunk_sweep.py); 850 MB of scratch
 
     // K-sdft plans, one per hop seen (tables depend on the hop); see select_sdft()
     struct SdftPlan {
@@ -1168,9 +1170,13 @@ struct EventPool {
 
 size_t segment_frames(const pvqt *v, size_t frames_in_batch)
 {
-    // a few segments per batch (copies overlap compute), at least 256 and at most one kernel chunk of frames each
+    // a few segments per batch (copies overlap compute), at least 256 frames each; at most segment_cap frames, so
+    // that the first H2D copy and the last D2H copy -- which nothing overlaps -- stay short in a long batch
+    // (2048 streams x 511 frames, pinned buffers: 17.7 / 18.5 / 18.8 / 18.5 M frames/s at 4096 / 8192 / 16384 / 32768,
+    // 16.5 M at 131072)
     const size_t n = v->segments_per_batch;
-    return std::min<size_t>(std::max<size_t>((frames_in_batch + n - 1) / n, 256), v->chunk_frames);
+    return std::min<size_t>(std::max<size_t>((frames_in_batch + n - 1) / n, 256),
+                            std::min<size_t>(v->segment_cap, v->chunk_frames));
 }
 
 // the copy streams join the compute stream's timeline (needed for graph capture, harmless otherwise)
@@ -1542,6 +1548,9 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
     if (const char *s = std::getenv("PVQT_HOST_LANES")) v->host_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
     if (const char *s = std::getenv("PVQT_SEGMENTS")) v->segments_per_batch = std::max(1, std::atoi(s));
     if (const char *s = std::getenv("PVQT_GRAPHS")) v->use_graphs = std::atoi(s) != 0;
+    if (const char *s = std::getenv("PVQT_SEGMENT_FRAMES")) v->segment_cap = (uint32_t)std::max(256, std::atoi(s));
+    if (const char *s = std::getenv("PVQT_CHUNK_FRAMES"))   // frames per launch (tuning); kept a multiple of two tiles
+        v->chunk_frames = (uint32_t)std::max(2 * kTileFrames, std::min(std::atoi(s), 1 << 20) / (2 * kTileFrames) * (2 * kTileFrames));
     if (const char *s = std::getenv("PVQT_SDFT_TC")) v->sdft_tc = std::max(0, std::min(std::atoi(s), 2));
     pvqt *raw = v.release();
     int rc = build_device_plan(raw);
@@ -1944,3 +1953,13 @@ int pvqt_multi_calc_streams_db(pvqt_multi *m, const float *audio, size_t n_strea
 }
 
 }  // extern "C"
+
+#ifdef PVQT_PHASE_TIMERS
+namespace pvqt_dev { cudaError_t read_phase_stamps(unsigned long long *out); }
+// Diagnostic build only: out[2][8192][8] globaltimer stamps (kernel 0 = K-fft, 1 = K-spmm-db) of the last launches.
+extern "C" int pvqt_debug_phase_stamps(unsigned long long *out)
+{
+    cudaDeviceSynchronize();
+    return pvqt_dev::read_phase_stamps(out) == cudaSuccess ? 0 : 7;
+}
+#endif

@@ -23,7 +23,26 @@
 
 #include <math_constants.h>
 
+#ifndef PVQT_FFT_MIN_BLOCKS
+#define PVQT_FFT_MIN_BLOCKS 1   // resident CTAs of 256 threads the register allocation of K-fft is held to
+#endif
+
 namespace pvqt_dev {
+#ifdef PVQT_PHASE_TIMERS
+// Diagnostic build only (scripts/phase_timers.py): globaltimer stamps per CTA and phase.
+__device__ unsigned long long g_phase_stamps[2][8192][8];
+#define PVQT_STAMP(kernel, slot)                                                                          \
+    do {                                                                                                  \
+        if (threadIdx.x == 0 && blockIdx.x < 8192) {                                                      \
+            unsigned long long t_;                                                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+            g_phase_stamps[kernel][blockIdx.x][slot] = t_;                                                \
+        }                                                                                                 \
+    } while (0)
+cudaError_t read_phase_stamps(unsigned long long *out) { return cudaMemcpyFromSymbol(out, g_phase_stamps, sizeof(g_phase_stamps)); }
+#else
+#define PVQT_STAMP(kernel, slot) do { } while (0)
+#endif
 namespace {
 
 constexpr float kSqrtHalf = 0.70710678118654752440f;
@@ -287,9 +306,10 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant__ FftParams P)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : 1) fft_groups_kernel(const __grid_constant__ FftParams P)
 {
     extern __shared__ __align__(16) float2 fft_smem[];
+    PVQT_STAMP(0, 0);
     pdl_launch_dependents();
     int gi = 0;
 #pragma unroll 1
@@ -314,6 +334,7 @@ __global__ void __launch_bounds__(BLOCK) fft_groups_kernel(const __grid_constant
 #undef PVQT_FFT_CASE
     default: break;
     }
+    PVQT_STAMP(0, 1);
     // Launched programmatically behind K-sdft (which runs beside this kernel): do not complete before it
     // has, so that the kernels after this one see the partial sums too.
     if (P.wait_prior) pdl_wait();
@@ -515,6 +536,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     extern __shared__ __align__(16) float4 fused_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile = blockIdx.x;
+    PVQT_STAMP(1, 0);
     const FusedWarp W = P.warp[warp];
     const int4 meta = __ldg(P.lane_meta + warp * 32 + lane);
     const int2 rows = __ldg(P.lane_rows + warp * 32 + lane);
@@ -537,7 +559,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     }
 
     pdl_launch_dependents();
+    PVQT_STAMP(1, 1);
     pdl_wait();  // everything above is plan data; the spectra below come from K-fft / K-sdft
+    PVQT_STAMP(1, 2);
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.spec) + (size_t)tile * P.spec_stride * 4;
         const int n16 = P.n_cols * 4;
@@ -576,6 +600,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     }
     cp_async_wait_all();
     __syncthreads();
+    PVQT_STAMP(1, 3);
 
     float2 re[ROWS][4], im[ROWS][4];
 #pragma unroll
@@ -631,6 +656,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
     const uint32_t frame0 = tile * kTileFrames;
     const int nb = P.n_buckets;
     __syncthreads();  // every warp is done reading the staged spectrum
+    PVQT_STAMP(1, 4);
     float *ls = reinterpret_cast<float *>(fused_smem);
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -646,6 +672,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
         }
     }
     __syncthreads();
+    PVQT_STAMP(1, 5);
 
     // power_to_db's frame-wise part (vqt.rs:933-950): one warp per frame, coalesced stores
     const int n_warps = blockDim.x >> 5;
@@ -688,6 +715,15 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
             for (int r = lane; r < nb; r += 32) out[r] = db_out(l[r], floor_db, log_spec_min);
         }
     }
+#ifdef PVQT_PHASE_TIMERS
+    __syncthreads();
+    PVQT_STAMP(1, 6);
+    if (threadIdx.x == 0 && blockIdx.x < 8192) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_phase_stamps[1][blockIdx.x][7] = sm;
+    }
+#endif
 }
 
 }  // namespace

@@ -380,8 +380,8 @@ def test_linearity_property_full_size(vqt):
 
 
 def test_config3_slice_many_streams(vqt, oracle_default):
-    """BASELINE configs[2] in small: 96 independent 10 s streams (511 frames each, 49,056 frames: several launch
-    chunks of 16 streams, K-sdft chunk rows of different streams sharing CTAs).  Every stream equals its own
+    """BASELINE configs[2] in small: 96 independent 10 s streams (511 frames each, 49,056 frames, K-sdft chunk rows of
+    different streams sharing CTAs).  Every stream equals its own
     single-recording call bit for bit; one stream is checked against the oracle."""
     base = [synth.polyphonic_chords(10.0, 22050.0, seed=100 + s) for s in range(6)]
     n = base[0].shape[0]
@@ -417,7 +417,7 @@ def test_config3_full_size_4096_streams(vqt, oracle_default):
     out = vqt.calculate_vqt_streams_in_db(streams, HOP)
     assert out.shape == (n_streams, 511, 588)
     assert np.isfinite(out).all() and out.min() >= 0.0
-    sample = [0, 1, 15, 16, 17, 2047, 2048, 4079, 4080, 4095]     # both sides of 16-stream launch chunks
+    sample = [0, 1, 15, 16, 255, 256, 257, 2047, 2048, 4079, 4080, 4095]     # both sides of launch chunks (256 streams)
     for s in sample:
         np.testing.assert_array_equal(out[s], vqt.calculate_vqt_batch_in_db(streams[s], HOP), err_msg=f"stream {s}")
     for s in (0, 2048, 4095):
@@ -431,9 +431,14 @@ def test_config3_full_size_4096_streams(vqt, oracle_default):
     np.testing.assert_array_equal(sums2, sums[perm])
 
 
-def test_long_recording_crosses_launch_chunks(vqt, oracle_default):
-    """One recording longer than a launch chunk (8192 frames): the device entry cuts it into frame ranges, each with
-    its own K-sdft chunk rows; results must not depend on where the cuts fall."""
+def test_long_recording_crosses_launch_chunks(built_lib, oracle_default, monkeypatch):
+    """One recording longer than a launch chunk (PVQT_CHUNK_FRAMES = 8192 here; the default is 131072): the device
+    entry cuts it into frame ranges, each with its own K-sdft chunk rows; results must not depend on where the cuts
+    fall."""
+    monkeypatch.setenv("PVQT_CHUNK_FRAMES", "8192")
+    vqt = pv.Vqt(pv.VqtParameters.default(), device=0)
+    monkeypatch.delenv("PVQT_CHUNK_FRAMES")
+    whole = pv.Vqt(pv.VqtParameters.default(), device=0)      # default chunk: one launch
     audio = synth.polyphonic_chords(175.0, 22050.0, seed=42)
     n_frames = synth.frames_in(audio.shape[0], vqt.n_fft, HOP)
     assert n_frames > 8192 + 1000
@@ -444,6 +449,8 @@ def test_long_recording_crosses_launch_chunks(vqt, oracle_default):
     dev = d_out.download((n_frames, 588))
     # the host entry cuts the same recording differently (copy/compute segments): same bits
     np.testing.assert_array_equal(vqt.calculate_vqt_batch_in_db(audio, HOP), dev)
+    # and so does a handle that runs the whole recording as one launch
+    np.testing.assert_array_equal(whole.calculate_vqt_batch_in_db(audio, HOP), dev)
     # frames around the cut against a call that starts elsewhere, and against the oracle
     t0 = 8192 - 40
     sub = vqt.calculate_vqt_batch_in_db(audio[t0 * HOP:], HOP, n_frames=80)
@@ -451,6 +458,8 @@ def test_long_recording_crosses_launch_chunks(vqt, oracle_default):
     for t in (8190, 8191, 8192, 8193, n_frames - 1):
         ref = oracle_default.calculate_vqt_instant_in_db(audio[t * HOP:t * HOP + vqt.n_fft], 0)
         assert np.abs(dev[t] - ref).max() <= TOL_DB, t
+    d_audio.free(); d_out.free()
+    vqt.close(); whole.close()
 
 
 def test_hires_config(built_lib):
