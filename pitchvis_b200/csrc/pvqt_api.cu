@@ -159,7 +159,11 @@ struct pvqt {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
         DeviceBuffer spec, power, sdft_c, sdft_r;
+        unsigned *sdft_done = nullptr;   // completion counter of the lane's K-sdft launches (device, 4 bytes)
+        uint32_t sdft_expected = 0;      // its value once every launch issued so far has finished
     } lane[kLanes];
+    bool early_combine = false;         // PVQT_EARLY_COMBINE=1: K-spmm-db starts its combine step on K-sdft's completion counter,
+                                        // before its grid wait (measured: no gain, 93.15 vs 93.18 us per step)
     cudaEvent_t lane_fork = nullptr;
     int host_lanes = 2;  // compute lanes of the pipelined host entries (PVQT_HOST_LANES)
     int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames
@@ -992,6 +996,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             float *spec = d_spec_out ? d_spec_out + (f0 / kTileFrames) * tile_elems : static_cast<float *>(L.spec.ptr);
 
             // ---- K-sdft partial sums ----
+            bool counted = true;   // every partial-sum launch of this range reports to the lane's completion counter
             std::vector<SdftParams> sd;
             std::vector<int> sd_plan;   // index into plan->groups / plan->tc
             for (int i : sdft_groups) {
@@ -1022,9 +1027,19 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                     sp.partial_c = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_c.ptr) + off);
                     sp.partial_r = reinterpret_cast<float2 *>(static_cast<char *>(L.sdft_r.ptr) + off);
                     off += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
+                    const bool on_tc = v->sdft_tc >= 1 && tc.n_groups > 0;
+                    // completion counter for K-spmm-db's early combine; not under graph capture (the expected value
+                    // would be baked into the graph) and not for the tcgen05 form
+                    sp.done_counter = nullptr;
+                    if (v->early_combine && !v->use_graphs && !on_tc && L.sdft_done != nullptr) {
+                        sp.done_counter = L.sdft_done;
+                        L.sdft_expected += sdft_partial_ctas(sp, v->sdft_tensor_cores);
+                    } else {
+                        counted = false;
+                    }
                     prof_begin(v, 4, stream);
-                    cudaError_t e = (v->sdft_tc >= 1 && tc.n_groups > 0) ? launch_sdft_partial_tc(sp, tc, stream)
-                                                                                 : launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
+                    cudaError_t e = on_tc ? launch_sdft_partial_tc(sp, tc, stream)
+                                          : launch_sdft_partial(sp, v->sdft_tensor_cores, stream);
                     if (e != cudaSuccess) return cuda_fail(e, "launch sdft_partial_kernel");
                     prof_end(v, stream);
                     v->launches.fetch_add(1);
@@ -1101,6 +1116,8 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 up.power = d_power ? d_power + f0 * nb : nullptr;
                 up.n_sdft = 0;
                 for (const auto &sp : sd) up.sdft[up.n_sdft++] = sp;
+                up.sdft_done = (!sd.empty() && counted) ? L.sdft_done : nullptr;
+                up.sdft_expected = L.sdft_expected;
                 prof_begin(v, 3, stream);
                 e = launch_spmm_db_fused(up, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_fused_kernel");
@@ -1538,10 +1555,15 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
         (e = cudaStreamCreateWithFlags(&v->s_out, cudaStreamNonBlocking)) != cudaSuccess)
         return cuda_error(e, "cudaStreamCreate");
 
-    for (auto &L : v->lane)
+    for (auto &L : v->lane) {
         if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
             return cuda_error(e, "create launch lanes");
+        if ((e = cudaMalloc(&L.sdft_done, sizeof(unsigned))) != cudaSuccess ||
+            (e = cudaMemset(L.sdft_done, 0, sizeof(unsigned))) != cudaSuccess)
+            return cuda_error(e, "allocate K-sdft completion counter");
+    }
+    if (const char *s = std::getenv("PVQT_EARLY_COMBINE")) v->early_combine = std::atoi(s) != 0;
     if ((e = cudaEventCreateWithFlags(&v->lane_fork, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_error(e, "create launch lanes");
     if (const char *s = std::getenv("PVQT_LANES")) v->n_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
@@ -1578,6 +1600,7 @@ void pvqt_destroy(pvqt *v)
     for (auto &L : v->lane) {
         if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         if (L.done) cudaEventDestroy(L.done);
+        if (L.sdft_done) cudaFree(L.sdft_done);
         L.spec.release(); L.power.release(); L.sdft_c.release(); L.sdft_r.release();
     }
     if (v->lane_fork) cudaEventDestroy(v->lane_fork);
@@ -1955,7 +1978,12 @@ int pvqt_multi_calc_streams_db(pvqt_multi *m, const float *audio, size_t n_strea
 }  // extern "C"
 
 #ifdef PVQT_PHASE_TIMERS
-namespace pvqt_dev { cudaError_t read_phase_stamps(unsigned long long *out); }
+namespace pvqt_dev { cudaError_t read_phase_stamps(unsigned long long *out); cudaError_t read_sdft_stamps(unsigned long long *out); }
+extern "C" int pvqt_debug_sdft_stamps(unsigned long long *out)
+{
+    cudaDeviceSynchronize();
+    return pvqt_dev::read_sdft_stamps(out) == cudaSuccess ? 0 : 7;
+}
 // Diagnostic build only: out[2][8192][8] globaltimer stamps (kernel 0 = K-fft, 1 = K-spmm-db) of the last launches.
 extern "C" int pvqt_debug_phase_stamps(unsigned long long *out)
 {

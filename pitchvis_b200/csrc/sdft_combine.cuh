@@ -11,13 +11,17 @@ namespace {
 
 // sum_i w[i * stride] * c[i * stride], i < n, as four interleaved partial sums (terms i mod 4) added at the
 // end: free, and half the rounding error of one running sum (DESIGN.md, K-sdft accuracy).
+// kCg: read the partial sums with ld.global.cg (L2 only) -- for the caller that starts on K-sdft's completion counter
+// instead of a grid dependency and must not meet a line an earlier kernel left in this SM's L1.
+template <bool kCg = false>
 __device__ __forceinline__ float2 sdft_dot(const float2 *c, const float2 *w, int n, int stride)
 {
+    auto ld = [](const float2 *p) { return kCg ? __ldcg(p) : *p; };
     float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     int i = 0;
     for (; i + 4 <= n; i += 4) {
         const float2 w0 = w[0], w1 = w[stride], w2 = w[2 * stride], w3 = w[3 * stride];
-        const float2 v0 = c[0], v1 = c[stride], v2 = c[2 * stride], v3 = c[3 * stride];
+        const float2 v0 = ld(c), v1 = ld(c + stride), v2 = ld(c + 2 * stride), v3 = ld(c + 3 * stride);
         w += 4 * stride;
         c += 4 * stride;
         a0 = __ffma2_rn(make_float2(w0.x, w0.x), v0, a0); a0 = __ffma2_rn(make_float2(-w0.y, w0.y), make_float2(v0.y, v0.x), a0);
@@ -26,7 +30,7 @@ __device__ __forceinline__ float2 sdft_dot(const float2 *c, const float2 *w, int
         a3 = __ffma2_rn(make_float2(w3.x, w3.x), v3, a3); a3 = __ffma2_rn(make_float2(-w3.y, w3.y), make_float2(v3.y, v3.x), a3);
     }
     for (; i < n; ++i) {
-        const float2 w0 = w[0], v0 = c[0];
+        const float2 w0 = w[0], v0 = ld(c);
         w += stride;
         c += stride;
         a0 = __ffma2_rn(make_float2(w0.x, w0.x), v0, a0); a0 = __ffma2_rn(make_float2(-w0.y, w0.y), make_float2(v0.y, v0.x), a0);

@@ -13,6 +13,10 @@
 #include "vqt_device.cuh"
 
 namespace pvqt_dev {
+#ifdef PVQT_PHASE_TIMERS
+__device__ unsigned long long g_sdft_stamps[1024][2];   // diagnostic build only (scripts/phase_timers.py)
+cudaError_t read_sdft_stamps(unsigned long long *out) { return cudaMemcpyFromSymbol(out, g_sdft_stamps, sizeof(g_sdft_stamps)); }
+#endif
 namespace {
 
 // 4-byte cp.async with zero fill: src_bytes = 0 writes zeros without reading.
@@ -139,6 +143,11 @@ __global__ void __launch_bounds__(kSdftThreads, 3) sdft_partial_kernel(const __g
                 P.partial_c[(size_t)row * G.nk + k] = acc[ch];
         }
     }
+    if (P.done_counter != nullptr) {   // publish: this CTA's sums are in global memory
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(P.done_counter, 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -185,6 +194,13 @@ __global__ void __launch_bounds__(kMmaThreads) sdft_partial_mma_kernel(const __g
     const uint32_t total_rows = P.n_streams * P.rows_per_stream;
     const uint32_t row0 = blockIdx.x * kMmaRowsPerCta;
 
+#ifdef PVQT_PHASE_TIMERS
+    if (tid == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        g_sdft_stamps[(blockIdx.y * gridDim.x + blockIdx.x) & 1023][0] = t_;
+    }
+#endif
     pdl_launch_dependents();
 
     if (tid < kMmaRowsPerCta) {
@@ -318,6 +334,18 @@ __global__ void __launch_bounds__(kMmaThreads) sdft_partial_mma_kernel(const __g
             if (row0 + g + 8 < total_rows) P.partial_c[(size_t)(row0 + g + 8) * G.nk + bin] = acc[q][1];
         }
     }
+    if (P.done_counter != nullptr) {   // publish: this CTA's sums are in global memory
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(P.done_counter, 1u);
+    }
+#ifdef PVQT_PHASE_TIMERS
+    if (tid == 0) {
+        unsigned long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        g_sdft_stamps[(blockIdx.y * gridDim.x + blockIdx.x) & 1023][1] = t_;
+    }
+#endif
 }
 
 // Stand-alone combine (one CTA per 8-frame tile); used when no K-fft launch follows the partial sums.
@@ -381,8 +409,20 @@ cudaError_t configure_sdft(int hop_pad)
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(sdft_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)kMmaRowsPerCta * (hop_pad + 4) * sizeof(float)));
+    // same L1 / shared-memory split as K-fft, which runs beside this kernel (vqt_kernels.cu, configure_kernels)
+    if (e == cudaSuccess && kStepCarveoutPct >= 0)
+        e = cudaFuncSetAttribute(sdft_partial_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveoutPct);
+    if (e == cudaSuccess && kStepCarveoutPct >= 0)
+        e = cudaFuncSetAttribute(sdft_partial_mma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveoutPct);
     if (e == cudaSuccess) configured[dev] = want;
     return e;
+}
+
+uint32_t sdft_partial_ctas(const SdftParams &p, bool tensor_cores)
+{
+    const uint32_t rows = p.n_streams * p.rows_per_stream;
+    const uint32_t per = tensor_cores ? kMmaRowsPerCta : kSdftRowsPerCta;
+    return ((rows + per - 1) / per) * (uint32_t)((p.g.nk + 63) / 64);
 }
 
 cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream)

@@ -94,6 +94,8 @@ struct SdftParams {
     float2      *partial_c;        // [n_streams * rows_per_stream][nk]
     float2      *partial_r;
     float       *spec;             // tiled planar layout; local frame = stream_local * frames + t
+    unsigned    *done_counter;     // optional: every CTA of the partial-sum kernel adds 1 when its sums are written
+                                   // (K-spmm-db starts its combine step on it, before K-fft has finished)
 };
 
 // Plan of the tcgen05 form of the partial sums (sdft_tc_kernel.cu): accumulation groups of 16-sample blocks.
@@ -199,6 +201,8 @@ struct FusedParams {
     float   *power;            // optional [n_frames][n_buckets]
     float    ref_db;
     int32_t  n_sdft;           // K-sdft groups whose combine step this kernel runs while it stages the tile
+    const unsigned *sdft_done; // completion counter of the partial-sum launches (nullptr: combine after the grid wait)
+    uint32_t sdft_expected;    // counter value once every partial-sum CTA of this launch has finished (modulo 2^32)
     SdftParams sdft[kMaxSdft];
 };
 
@@ -251,12 +255,17 @@ constexpr int kClusterPlaneCols = 384;   // columns per chunk plane of a staged 
 constexpr int kClusterThreads = 384;     // 12 warps: up to 96 row pairs per part; two CTAs share an SM
 constexpr int kClusterRoundFrames = 2 * kTileFrames;
 
+#ifndef PVQT_STEP_CARVEOUT_PCT
+#define PVQT_STEP_CARVEOUT_PCT 72
+#endif
+constexpr int kStepCarveoutPct = PVQT_STEP_CARVEOUT_PCT;   // shared-memory carve-out (% of 228 KB) of K-sdft and K-fft; -1: driver's choice
 constexpr int kFusedRing = 4;   // coefficient slots the one-CTA-per-tile K-spmm-db keeps in flight per lane
 constexpr int kSpmmWarps = 4;   // warps (= tiles) per SpMM CTA
 constexpr int kSpmmUnroll = 4;  // band slots per software-pipeline group (band widths are padded to it)
 
 cudaError_t launch_fft(const FftParams &p, int total_ctas, int block_threads, cudaStream_t stream);
 cudaError_t launch_sdft_partial(const SdftParams &p, bool tensor_cores, cudaStream_t stream);
+uint32_t    sdft_partial_ctas(const SdftParams &p, bool tensor_cores);   // CTAs of that launch (each adds 1 to done_counter)
 cudaError_t launch_sdft_combine(const SdftParams &p, cudaStream_t stream);
 bool        sdft_tc_supported(const SdftGroup &g);          // sdft_tc_kernel.cu: the tcgen05 form of the partial sums
 void        sdft_tc_make_plan(const SdftGroup &g, int group16, SdftTcPlan *t);

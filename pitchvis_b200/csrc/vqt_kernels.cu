@@ -24,7 +24,7 @@
 #include <math_constants.h>
 
 #ifndef PVQT_FFT_MIN_BLOCKS
-#define PVQT_FFT_MIN_BLOCKS 1   // resident CTAs of 256 threads the register allocation of K-fft is held to
+#define PVQT_FFT_MIN_BLOCKS 4   // resident CTAs of 256 threads the register allocation of K-fft is held to
 #endif
 
 namespace pvqt_dev {
@@ -159,12 +159,29 @@ __host__ __device__ constexpr int plan_radix(int nc, int pass)
 __host__ __device__ constexpr int pad_index(int i) { return i + (i >> 4); }
 
 // Barrier among the T threads that share one FFT (several FFTs share a CTA when T < BLOCK).
+// The barrier id must be an immediate: with `bar.sync %r, T` ptxas reserves all 16 named barriers for the CTA, and
+// named barriers are an SM-wide pool -- K-fft then ran 2 CTAs per SM instead of the 4 its registers allow
+// (globaltimer stamps per CTA, scripts/phase_timers.py).  With immediates a 256-thread CTA uses at most 5.
+template <int T, int ID, int N>
+__device__ __forceinline__ void fft_bar_case(int fid)
+{
+    if constexpr (ID + 1 < N) {
+        if (fid == ID) asm volatile("bar.sync %0, %1;" ::"n"((ID + 1) & 15), "n"(T) : "memory");
+        else fft_bar_case<T, ID + 1, N>(fid);
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"n"((ID + 1) & 15), "n"(T) : "memory");
+    }
+}
 template <int T, int BLOCK>
 __device__ __forceinline__ void fft_sync(int fid)
 {
     if constexpr (T >= BLOCK || T < 32) __syncthreads();
     else if constexpr (T == 32) __syncwarp();
+#ifdef PVQT_FFT_OLD_BAR   // A/B only
     else asm volatile("bar.sync %0, %1;" ::"r"(fid + 1), "n"(T) : "memory");
+#else
+    else fft_bar_case<T, 0, BLOCK / T>(fid);
+#endif
 }
 
 // One Stockham pass (decimation in time, autosort):
@@ -335,14 +352,29 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : 1)
     default: break;
     }
     PVQT_STAMP(0, 1);
-    // Launched programmatically behind K-sdft (which runs beside this kernel): do not complete before it
-    // has, so that the kernels after this one see the partial sums too.
+#ifdef PVQT_PHASE_TIMERS
+    if (threadIdx.x == 0 && blockIdx.x < 8192) {
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_phase_stamps[0][blockIdx.x][2] = sm;
+        g_phase_stamps[0][blockIdx.x][3] = gi;
+    }
+#endif
+    // Launched programmatically behind K-sdft (which runs beside this kernel): the grid must not complete before
+    // that one has, so that the kernels after this one see the partial sums too.  One CTA -- the last one, which
+    // starts when K-sdft is long complete -- waits for the whole grid: with the wait in every CTA the first wave
+    // (2 CTAs per SM beside K-sdft's) finished its FFTs after 4 us and then held its SM slots until K-sdft ended
+    // at 16 us, with no K-fft CTA running in between (globaltimer stamps, scripts/phase_timers.py).
+#ifndef PVQT_FFT_WAIT_ALL
+    if (P.wait_prior && blockIdx.x == gridDim.x - 1) pdl_wait();
+#else
     if (P.wait_prior) pdl_wait();
+#endif
     // The CTAs of one FFT group also run the combine step of the K-sdft groups for the frames they own,
     // reusing the FFT's shared memory.  The host picks the last group: its CTAs are scheduled when the
     // partial sums are long complete, so the wait below never holds SM slots.
     if (P.n_sdft > 0 && gi == P.combine_group) {
-        if (!P.wait_prior) pdl_wait();
+        pdl_wait();   // the partial sums must be complete (a second wait in the last CTA is harmless)
         __syncthreads();
         const uint32_t lf0 = (blockIdx.x - g.cta_begin) * g.frames_per_cta;
         for (int i = 0; i < P.n_sdft; ++i)
@@ -560,7 +592,56 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
 
     pdl_launch_dependents();
     PVQT_STAMP(1, 1);
-    pdl_wait();  // everything above is plan data; the spectra below come from K-fft / K-sdft
+
+    // K-sdft combine for this tile, straight into the planes (the columns of those groups are not in `spec`):
+    // X_t[k] = sum_i phase[i][k] C[row(t) + i][k] (+ remainder), every CTA its own 8 frames.  As an epilogue of
+    // K-fft's last CTAs the same step cost 8 us of that kernel's tail.
+    auto combine = [&]() {
+        for (int gi = 0; gi < P.n_sdft; ++gi) {
+            const SdftParams &D = P.sdft[gi];
+            const SdftGroup &G = D.g;
+            const uint32_t lf0 = tile * kTileFrames, total = D.n_streams * D.frames;
+            const int items = kTileFrames * G.nk;
+            for (int item = threadIdx.x; item < items; item += blockDim.x) {
+                const int fi = item / G.nk, k = item - fi * G.nk;
+                const uint32_t lf = lf0 + fi;
+                float2 x = make_float2(0.f, 0.f);
+                if (lf < total) {
+                    const uint32_t st = lf / D.frames, t = lf - st * D.frames;
+                    const size_t row = (size_t)st * D.rows_per_stream + t;
+                    x = sdft_dot<true>(D.partial_c + row * G.nk + k, G.phase + k, G.q, G.nk);
+                    if (G.rem != 0) x = __fadd2_rn(x, cmul(__ldcg(D.partial_r + (row + G.q) * G.nk + k), __ldg(G.phase + G.q * G.nk + k)));
+                }
+                float *re_plane = reinterpret_cast<float *>(fused_smem + (fi >> 2) * PLANE + G.spec_offset + k);
+                float *im_plane = reinterpret_cast<float *>(fused_smem + (2 + (fi >> 2)) * PLANE + G.spec_offset + k);
+                re_plane[fi & 3] = x.x;
+                im_plane[fi & 3] = x.y;
+            }
+        }
+    };
+    // The partial sums come from K-sdft, which ended long before K-fft does: when its completion counter says so,
+    // the combine runs here, beside K-fft's last CTAs, instead of after the grid-wide wait.  The poll is bounded --
+    // if the counter is not there in time the combine runs after the wait, where the grid dependency covers it.
+    bool early = false;
+    if (P.n_sdft > 0 && P.sdft_done != nullptr) {
+        __shared__ int sdft_ready;
+        if (threadIdx.x == 0) {
+            int ok = 0;
+            for (int tries = 0; tries < 64 && !ok; ++tries) {
+                unsigned seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.sdft_done) : "memory");
+                ok = (int)(seen - P.sdft_expected) >= 0;
+                if (!ok) __nanosleep(200);
+            }
+            sdft_ready = ok;
+        }
+        __syncthreads();
+        early = sdft_ready != 0;
+        if (early) combine();
+    }
+    PVQT_STAMP(1, 7);
+
+    pdl_wait();  // everything above is plan data or K-sdft's; the spectra below come from K-fft
     PVQT_STAMP(1, 2);
     {
         const float4 *src = reinterpret_cast<const float4 *>(P.spec) + (size_t)tile * P.spec_stride * 4;
@@ -568,36 +649,13 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
         for (int i = threadIdx.x; i < n16; i += blockDim.x) {
             const int c = i >> 2, p = i & 3;     // physical chunk p of column c
             const int q = p ^ ((c >> 1) & 3);    // logical chunk: 0,1 = Re frames 0-3, 4-7; 2,3 = Im
-            bool from_sdft = false;              // columns the combine below produces are not copied
+            bool from_sdft = false;              // columns the combine produces are not copied
             for (int gi = 0; gi < P.n_sdft; ++gi)
                 from_sdft |= c >= P.sdft[gi].g.spec_offset && c < P.sdft[gi].g.spec_offset + P.sdft[gi].g.nk;
             if (!from_sdft) cp_async16(fused_smem + q * PLANE + c, src + i);
         }
     }
-    // K-sdft combine for this tile, straight into the planes (the columns of those groups are not in `spec`):
-    // X_t[k] = sum_i phase[i][k] C[row(t) + i][k] (+ remainder), every CTA its own 8 frames, while the cp.async
-    // copies above are in flight.  As an epilogue of K-fft's last CTAs the same step cost 8 us of that kernel's tail.
-    for (int gi = 0; gi < P.n_sdft; ++gi) {
-        const SdftParams &D = P.sdft[gi];
-        const SdftGroup &G = D.g;
-        const uint32_t lf0 = tile * kTileFrames, total = D.n_streams * D.frames;
-        const int items = kTileFrames * G.nk;
-        for (int item = threadIdx.x; item < items; item += blockDim.x) {
-            const int fi = item / G.nk, k = item - fi * G.nk;
-            const uint32_t lf = lf0 + fi;
-            float2 x = make_float2(0.f, 0.f);
-            if (lf < total) {
-                const uint32_t st = lf / D.frames, t = lf - st * D.frames;
-                const size_t row = (size_t)st * D.rows_per_stream + t;
-                x = sdft_dot(D.partial_c + row * G.nk + k, G.phase + k, G.q, G.nk);
-                if (G.rem != 0) x = __fadd2_rn(x, cmul(D.partial_r[(row + G.q) * G.nk + k], __ldg(G.phase + G.q * G.nk + k)));
-            }
-            float *re_plane = reinterpret_cast<float *>(fused_smem + (fi >> 2) * PLANE + G.spec_offset + k);
-            float *im_plane = reinterpret_cast<float *>(fused_smem + (2 + (fi >> 2)) * PLANE + G.spec_offset + k);
-            re_plane[fi & 3] = x.x;
-            im_plane[fi & 3] = x.y;
-        }
-    }
+    if (!early) combine();   // while the cp.async copies above are in flight
     cp_async_wait_all();
     __syncthreads();
     PVQT_STAMP(1, 3);
@@ -718,11 +776,6 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
 #ifdef PVQT_PHASE_TIMERS
     __syncthreads();
     PVQT_STAMP(1, 6);
-    if (threadIdx.x == 0 && blockIdx.x < 8192) {
-        unsigned sm;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-        g_phase_stamps[1][blockIdx.x][7] = sm;
-    }
 #endif
 }
 
@@ -745,6 +798,15 @@ cudaError_t configure_kernels(int max_cols)
                                   (int)fft_smem_bytes(512))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_groups_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fft_smem_bytes(1024))) != cudaSuccess) return e;
+    // K-fft runs beside K-sdft (programmatic dependent launch).  CTAs of two kernels share an SM only under the same
+    // L1 / shared-memory split, and the driver derives each kernel's split from its own occupancy: with K-fft at
+    // 4 CTAs per SM (143 KB) and K-sdft at 100 KB, K-fft's CTAs waited until K-sdft had left the SMs (13 us; globaltimer
+    // stamps, scripts/phase_timers.py).  Both kernels therefore name the same carve-out (kStepCarveoutPct, 164 KB).
+    if (kStepCarveoutPct >= 0)
+        for (const void *k : {(const void *)fft_groups_kernel<256>, (const void *)fft_groups_kernel<512>,
+                              (const void *)fft_groups_kernel<1024>})
+            if ((e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, kStepCarveoutPct)) != cudaSuccess)
+                return e;
     if (spmm_smem_bytes(max_cols) > 227 * 1024) return cudaErrorInvalidConfiguration;
     return cudaFuncSetAttribute(spmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)spmm_smem_bytes(max_cols));
