@@ -434,7 +434,38 @@ int build_fused_plan(pvqt *v)
         }
         first_row += g.filter_bank.rows;
     }
-    std::stable_sort(units.begin(), units.end(), [](const Unit &a, const Unit &b) { return a.len + a.nlen > b.len + b.nlen; });
+    // Order of the units = which 32 share a warp.  A warp walks max(len) + max(nlen) slots, so units are sorted by band
+    // length, and the few units with a conjugate-part band (38 of 294 at the defaults) stay together: they go in as
+    // one block, at the position of the length-sorted list that minimises the sum of the warps' walks (at the
+    // defaults 408 slots per tile instead of the 435 of sorting by len + nlen).  Per-row arithmetic is unchanged.
+    {
+        std::vector<Unit> pos, neg;
+        for (const Unit &u : units) (u.nlen > 0 ? neg : pos).push_back(u);
+        auto by_len = [](const Unit &a, const Unit &b) { return a.len > b.len; };
+        std::stable_sort(pos.begin(), pos.end(), by_len);
+        std::stable_sort(neg.begin(), neg.end(), by_len);
+        auto walk_slots = [&](size_t at) {
+            long total = 0;
+            int w = 0, nw = 0;
+            const size_t n = pos.size() + neg.size();
+            for (size_t i = 0; i < n; ++i) {
+                const Unit &u = i < at ? pos[i] : (i < at + neg.size() ? neg[i - at] : pos[i - neg.size()]);
+                w = std::max(w, u.len);
+                nw = std::max(nw, u.nlen);
+                if ((i & 31) == 31 || i + 1 == n) { total += w + nw; w = nw = 0; }
+            }
+            return total;
+        };
+        size_t best_at = 0;
+        long best = -1;
+        for (size_t at = 0; at <= pos.size(); ++at) {
+            const long c = walk_slots(at);
+            if (best < 0 || c < best) { best = c; best_at = at; }
+        }
+        units.assign(pos.begin(), pos.begin() + (long)best_at);
+        units.insert(units.end(), neg.begin(), neg.end());
+        units.insert(units.end(), pos.begin() + (long)best_at, pos.end());
+    }
     const int n_warps = (int)((units.size() + 31) / 32);
     n_cols = std::min<int>((n_cols + 7) & ~7, F.spec_stride);
     // columns the unpredicated band walk may read: start column + the warp's (padded) width; bounded by

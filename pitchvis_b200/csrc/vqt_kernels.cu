@@ -323,7 +323,7 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : 1) fft_groups_kernel(const __grid_constant__ FftParams P)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : (BLOCK == 512 ? 2 : 1)) fft_groups_kernel(const __grid_constant__ FftParams P)
 {
     extern __shared__ __align__(16) float2 fft_smem[];
     PVQT_STAMP(0, 0);
