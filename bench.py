@@ -280,6 +280,16 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # Only the JSON line goes to stdout: libraries that print there (NCCL's version banner under NCCL_DEBUG=VERSION)
+    # are sent to stderr by pointing fd 1 at fd 2 for the rest of the run; `emit` writes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     dist = None
     if world > 1:
         import torch
@@ -468,7 +478,7 @@ def main():
         elif not args.no_cpu_baseline:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "measured at N=1 only"}
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     for e in ev:
         lib.pvqt_event_destroy(h, e)

@@ -297,6 +297,21 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
     const uint64_t stream = f / P.frames.frames_per_stream;
     const uint64_t in_stream = f - stream * P.frames.frames_per_stream;
     const float *x = P.frames.audio + stream * P.frames.stream_stride + in_stream * P.frames.hop + g.window_begin;
+    // The nested windows are centred, so at the defaults every window starts on an odd sample and the packed loads
+    // z[m] = (x[2m], x[2m+1]) would be 4-byte loads.  Transform the window moved one sample down instead (8-byte
+    // aligned) and undo the shift on the consumed bins in the split step:
+    //   X[k] = W^-k (X'[k] + x[w + N - 1] - x[w - 1]),   W = exp(-2 pi i / N)
+    // (exact algebra: the two windows differ by one sample at either end, and W^(N k) = 1).
+#ifndef PVQT_FFT_NO_SHIFT
+    const bool shifted = (reinterpret_cast<uintptr_t>(x) & 7) != 0 && g.window_begin >= 1;
+#else
+    const bool shifted = false;
+#endif
+    float edge = 0.f;
+    if (shifted) {
+        x -= 1;
+        if (valid) edge = __ldg(x + 2 * NC) - __ldg(x);
+    }
 
     float2 *s = smem + fid * pad_index(NC);
     float2 v[kPointsPerThread];
@@ -315,7 +330,8 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
             const float2 d = __fmul2_rn(__fadd2_rn(zk, make_float2(-zn.x, zn.y)), make_float2(0.5f, 0.5f));
             const float2 o = cmul_mi(d);
             const float2 w = __ldg(g.split_twiddle + i);
-            const float2 xc = cadd(e, cmul(o, w));
+            float2 xc = cadd(e, cmul(o, w));
+            if (shifted) xc = cmul(make_float2(xc.x + edge, xc.y), make_float2(w.x, -w.y));   // W^-c = conj(w)
             P.spec[spec_index_re(local_frame, g.spec_offset + i, P.spec_stride)] = xc.x;
             P.spec[spec_index_im(local_frame, g.spec_offset + i, P.spec_stride)] = xc.y;
         }
