@@ -158,12 +158,12 @@ struct pvqt {
     struct Lane {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        DeviceBuffer spec, power, sdft_c, sdft_r;
+        DeviceBuffer spec, power, sdft_c, sdft_r, tile_ready;
         unsigned *sdft_done = nullptr;   // completion counter of the lane's K-sdft launches (device, 4 bytes)
         uint32_t sdft_expected = 0;      // its value once every launch issued so far has finished
     } lane[kLanes];
-    bool early_combine = false;         // PVQT_EARLY_COMBINE=1: K-spmm-db starts its combine step on K-sdft's completion counter,
-                                        // before its grid wait (measured: no gain, 93.15 vs 93.18 us per step)
+    bool tile_flags = true;             // PVQT_TILE_FLAGS=0: K-spmm-db waits for the whole K-fft grid instead of for the
+                                        // completion counters of K-sdft and of the K-fft CTAs that write its tile
     cudaEvent_t lane_fork = nullptr;
     int host_lanes = 2;  // compute lanes of the pipelined host entries (PVQT_HOST_LANES)
     int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames
@@ -1062,7 +1062,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                     // completion counter for K-spmm-db's early combine; not under graph capture (the expected value
                     // would be baked into the graph) and not for the tcgen05 form
                     sp.done_counter = nullptr;
-                    if (v->early_combine && !v->use_graphs && !on_tc && L.sdft_done != nullptr) {
+                    if (v->tile_flags && !v->use_graphs && !on_tc && L.sdft_done != nullptr) {
                         sp.done_counter = L.sdft_done;
                         L.sdft_expected += sdft_partial_ctas(sp, v->sdft_tensor_cores);
                     } else {
@@ -1097,6 +1097,19 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             }
             fp.n_groups = kept;
             fp.n_sdft = 0;
+            // per-tile completion counts for K-spmm-db (one-CTA form only; not under graph capture; K-sdft must report too)
+            const bool flags = v->tile_flags && !v->use_graphs && v->fused_ok && !v->cluster_ok && !d_spec_out &&
+                               kept > 0 && counted;
+            fp.tile_ready = nullptr;
+            if (flags) {
+                const size_t want = ((size_t)n / kTileFrames + 2) * sizeof(unsigned);
+                if (want > L.tile_ready.bytes) {
+                    if (L.tile_ready.reserve(std::max<size_t>(want, 4096)) != cudaSuccess)
+                        return cuda_fail(cudaGetLastError(), "allocate tile counters");
+                    PVQT_CUDA(cudaMemsetAsync(L.tile_ready.ptr, 0, L.tile_ready.bytes, stream));  // K-spmm-db leaves them at zero
+                }
+                fp.tile_ready = static_cast<unsigned *>(L.tile_ready.ptr);
+            }
             // the combine step runs inside K-spmm-db (one-CTA form); K-fft's last CTAs take it over for the other
             // SpMM forms and for the spectra test hook
             const bool combine_in_spmm = v->fused_ok && !v->cluster_ok && !d_spec_out;
@@ -1149,6 +1162,9 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 for (const auto &sp : sd) up.sdft[up.n_sdft++] = sp;
                 up.sdft_done = (!sd.empty() && counted) ? L.sdft_done : nullptr;
                 up.sdft_expected = L.sdft_expected;
+                up.tile_ready = fp.tile_ready;
+                up.n_ready_groups = fp.n_groups;
+                for (int g = 0; g < fp.n_groups; ++g) up.ready_fpc[g] = fp.group[g].frames_per_cta;
                 prof_begin(v, 3, stream);
                 e = launch_spmm_db_fused(up, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_fused_kernel");
@@ -1594,7 +1610,7 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
             (e = cudaMemset(L.sdft_done, 0, sizeof(unsigned))) != cudaSuccess)
             return cuda_error(e, "allocate K-sdft completion counter");
     }
-    if (const char *s = std::getenv("PVQT_EARLY_COMBINE")) v->early_combine = std::atoi(s) != 0;
+    if (const char *s = std::getenv("PVQT_TILE_FLAGS")) v->tile_flags = std::atoi(s) != 0;
     if ((e = cudaEventCreateWithFlags(&v->lane_fork, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_error(e, "create launch lanes");
     if (const char *s = std::getenv("PVQT_LANES")) v->n_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));

@@ -118,6 +118,8 @@ struct FftParams {
     int32_t     wait_prior;   // 1: launched programmatically behind K-sdft, wait for it before exiting
     int32_t     n_sdft;       // K-sdft groups whose combine step the CTAs of FFT group `combine_group` run
     int32_t     combine_group;
+    unsigned   *tile_ready;   // optional [ceil(n_frames / 8)]: every CTA adds 1 to each tile it has written its frames of
+                              // (K-spmm-db starts on a tile's count instead of on the whole grid; it resets the count)
     SdftParams  sdft[kMaxSdft];     // (see sdft_combine.cuh)
 };
 
@@ -203,6 +205,9 @@ struct FusedParams {
     int32_t  n_sdft;           // K-sdft groups whose combine step this kernel runs while it stages the tile
     const unsigned *sdft_done; // completion counter of the partial-sum launches (nullptr: combine after the grid wait)
     uint32_t sdft_expected;    // counter value once every partial-sum CTA of this launch has finished (modulo 2^32)
+    unsigned *tile_ready;      // per-tile count of K-fft CTAs that have written the tile (nullptr: wait for the grid)
+    int32_t  n_ready_groups;   // window groups on the FFT path and the frames one K-fft CTA covers in each
+    int32_t  ready_fpc[kMaxGroups];
     SdftParams sdft[kMaxSdft];
 };
 

@@ -376,6 +376,17 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : (B
         g_phase_stamps[0][blockIdx.x][3] = gi;
     }
 #endif
+    // Tell K-spmm-db which tiles are complete: it then starts on a tile while other CTAs of this grid still run,
+    // instead of after the grid and its flush (3 us after the last CTA, and all its CTAs in lock-step).
+    if (P.tile_ready != nullptr) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t lf0 = (blockIdx.x - g.cta_begin) * g.frames_per_cta;
+            const uint32_t lf1 = min(lf0 + (uint32_t)g.frames_per_cta, P.frames.n_frames);
+            for (uint32_t tl = lf0 / kTileFrames; tl * kTileFrames < lf1; ++tl) atomicAdd(P.tile_ready + tl, 1u);
+        }
+    }
     // Launched programmatically behind K-sdft (which runs beside this kernel): the grid must not complete before
     // that one has, so that the kernels after this one see the partial sums too.  One CTA -- the last one, which
     // starts when K-sdft is long complete -- waits for the whole grid: with the wait in every CTA the first wave
@@ -635,31 +646,28 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
             }
         }
     };
-    // The partial sums come from K-sdft, which ended long before K-fft does: when its completion counter says so,
-    // the combine runs here, beside K-fft's last CTAs, instead of after the grid-wide wait.  The poll is bounded --
-    // if the counter is not there in time the combine runs after the wait, where the grid dependency covers it.
-    bool early = false;
-    if (P.n_sdft > 0 && P.sdft_done != nullptr) {
-        __shared__ int sdft_ready;
+    // Dependencies.  By default the kernel waits for the grid before it (K-fft, which itself outlasts K-sdft).  With
+    // the completion counters armed it instead waits for exactly what this tile needs -- K-sdft's partial sums for
+    // the combine, then the K-fft CTAs that write this tile -- so the CTAs of a step no longer start in lock-step
+    // 3 us after K-fft's last CTA.  Every poll is bounded and falls back to the grid wait.
+    __shared__ int dep_ready;
+    auto poll = [&](auto done, int tries) {   // thread 0 polls, the CTA learns the outcome
         if (threadIdx.x == 0) {
             int ok = 0;
-            for (int tries = 0; tries < 64 && !ok; ++tries) {
-                unsigned seen;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.sdft_done) : "memory");
-                ok = (int)(seen - P.sdft_expected) >= 0;
-                if (!ok) __nanosleep(200);
-            }
-            sdft_ready = ok;
+            for (int i = 0; i < tries && !(ok = done()); ++i) __nanosleep(100);
+            dep_ready = ok;
         }
         __syncthreads();
-        early = sdft_ready != 0;
-        if (early) combine();
-    }
-    PVQT_STAMP(1, 7);
-
-    pdl_wait();  // everything above is plan data or K-sdft's; the spectra below come from K-fft
-    PVQT_STAMP(1, 2);
-    {
+        const bool r = dep_ready != 0;
+        __syncthreads();
+        return r;
+    };
+    auto load_acquire = [](const unsigned *p) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    };
+    auto stage = [&]() {
         const float4 *src = reinterpret_cast<const float4 *>(P.spec) + (size_t)tile * P.spec_stride * 4;
         const int n16 = P.n_cols * 4;
         for (int i = threadIdx.x; i < n16; i += blockDim.x) {
@@ -670,8 +678,32 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) spmm_db_fused_kernel(
                 from_sdft |= c >= P.sdft[gi].g.spec_offset && c < P.sdft[gi].g.spec_offset + P.sdft[gi].g.nk;
             if (!from_sdft) cp_async16(fused_smem + q * PLANE + c, src + i);
         }
+    };
+    if (P.tile_ready == nullptr) {
+        pdl_wait();  // everything above is plan data; the spectra and partial sums below come from K-fft / K-sdft
+        PVQT_STAMP(1, 2);
+        stage();
+        combine();   // while the cp.async copies are in flight
+    } else {
+        bool waited = false;
+        if (P.n_sdft > 0) {
+            const bool ok = P.sdft_done != nullptr &&
+                            poll([&] { return (int)(load_acquire(P.sdft_done) - P.sdft_expected) >= 0; }, 256);
+            if (!ok) { pdl_wait(); waited = true; }
+            combine();
+        }
+        PVQT_STAMP(1, 7);
+        if (!waited) {
+            const uint32_t nf = min((uint32_t)kTileFrames, P.n_frames - tile * kTileFrames);
+            uint32_t expected = 0;
+            for (int gi = 0; gi < P.n_ready_groups; ++gi)
+                expected += P.ready_fpc[gi] >= kTileFrames ? 1u : (nf + P.ready_fpc[gi] - 1) / P.ready_fpc[gi];
+            if (!poll([&] { return load_acquire(P.tile_ready + tile) == expected; }, 4096)) pdl_wait();
+        }
+        if (threadIdx.x == 0) P.tile_ready[tile] = 0;   // every writer of this tile is through: reset for the next launch
+        PVQT_STAMP(1, 2);
+        stage();
     }
-    if (!early) combine();   // while the cp.async copies above are in flight
     cp_async_wait_all();
     __syncthreads();
     PVQT_STAMP(1, 3);

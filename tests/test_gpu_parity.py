@@ -462,6 +462,26 @@ def test_long_recording_crosses_launch_chunks(built_lib, oracle_default, monkeyp
     vqt.close(); whole.close()
 
 
+def test_tile_flags_do_not_change_results(built_lib, vqt, chords, monkeypatch):
+    """K-spmm-db starts a tile on the completion counts of K-sdft and of the K-fft CTAs that write it (default) or
+    on the whole K-fft grid (PVQT_TILE_FLAGS=0): same bits, for a batch with a partial last tile, for short streams
+    that share tiles, and when the same handle is used again (the counts must be back at zero)."""
+    monkeypatch.setenv("PVQT_TILE_FLAGS", "0")
+    plain = pv.Vqt(pv.VqtParameters.default(), device=0)
+    monkeypatch.delenv("PVQT_TILE_FLAGS")
+    audio = chords[:vqt.n_fft + 1002 * HOP]                      # 1003 frames: the last tile holds 3
+    n = vqt.n_fft + 20 * HOP
+    streams = np.stack([chords[o:o + n] for o in (0, 5000, 9999, 30001, 41234, 50000, 61000)])   # 21 frames each
+    want = plain.calculate_vqt_batch_in_db(audio, HOP)
+    want_s = plain.calculate_vqt_streams_in_db(streams, HOP)
+    for _ in range(3):
+        np.testing.assert_array_equal(vqt.calculate_vqt_batch_in_db(audio, HOP), want)
+        np.testing.assert_array_equal(vqt.calculate_vqt_streams_in_db(streams, HOP), want_s)
+    one = vqt.calculate_vqt_batch_in_db(audio[:vqt.n_fft], HOP)   # a single frame (FFT path only)
+    np.testing.assert_array_equal(one, plain.calculate_vqt_batch_in_db(audio[:vqt.n_fft], HOP))
+    plain.close()
+
+
 def test_hires_config(built_lib):
     # BASELINE configs[3]: more buckets per octave, an extra octave, 2x FFT window
     v = pv.Vqt(pv.VqtParameters.hires())
