@@ -162,8 +162,8 @@ struct pvqt {
         unsigned *sdft_done = nullptr;   // completion counter of the lane's K-sdft launches (device, 4 bytes)
         uint32_t sdft_expected = 0;      // its value once every launch issued so far has finished
     } lane[kLanes];
-    bool tile_flags = true;             // PVQT_TILE_FLAGS=0: K-spmm-db waits for the whole K-fft grid instead of for the
-                                        // completion counters of K-sdft and of the K-fft CTAs that write its tile
+    bool tile_flags = false;            // PVQT_TILE_FLAGS=1: K-spmm-db starts a tile on the completion counters of K-sdft and of
+                                        // the K-fft CTAs that write the tile, instead of on the whole K-fft grid
     cudaEvent_t lane_fork = nullptr;
     int host_lanes = 2;  // compute lanes of the pipelined host entries (PVQT_HOST_LANES)
     int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames

@@ -463,11 +463,13 @@ def test_long_recording_crosses_launch_chunks(built_lib, oracle_default, monkeyp
 
 
 def test_tile_flags_do_not_change_results(built_lib, vqt, chords, monkeypatch):
-    """K-spmm-db starts a tile on the completion counts of K-sdft and of the K-fft CTAs that write it (default) or
-    on the whole K-fft grid (PVQT_TILE_FLAGS=0): same bits, for a batch with a partial last tile, for short streams
-    that share tiles, and when the same handle is used again (the counts must be back at zero)."""
+    """K-spmm-db starts a tile on the completion counts of K-sdft and of the K-fft CTAs that write it
+    (PVQT_TILE_FLAGS=1) or on the whole K-fft grid (0): same bits, for a batch with a partial last tile, for short
+    streams that share tiles, and when the same handle is used again (the counts must be back at zero)."""
     monkeypatch.setenv("PVQT_TILE_FLAGS", "0")
     plain = pv.Vqt(pv.VqtParameters.default(), device=0)
+    monkeypatch.setenv("PVQT_TILE_FLAGS", "1")
+    vqt = pv.Vqt(pv.VqtParameters.default(), device=0)
     monkeypatch.delenv("PVQT_TILE_FLAGS")
     audio = chords[:vqt.n_fft + 1002 * HOP]                      # 1003 frames: the last tile holds 3
     n = vqt.n_fft + 20 * HOP
@@ -480,6 +482,7 @@ def test_tile_flags_do_not_change_results(built_lib, vqt, chords, monkeypatch):
     one = vqt.calculate_vqt_batch_in_db(audio[:vqt.n_fft], HOP)   # a single frame (FFT path only)
     np.testing.assert_array_equal(one, plain.calculate_vqt_batch_in_db(audio[:vqt.n_fft], HOP))
     plain.close()
+    vqt.close()
 
 
 def test_hires_config(built_lib):
