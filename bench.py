@@ -191,20 +191,33 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     import orc
+    threads = host_threads()
     if args.workload == "streams4096":
-        # bounded sample of config 3: the first 16 streams of the 4096 (same frames-per-stream, same parameters)
-        params, audio, hop, n_streams, fps_ = workload(args.workload, seed=0, rank=0, world=args.streams // 16,
+        # bounded sample of config 3: the first 2 x threads streams of the 4096 (same frames per stream, same
+        # parameters); one host thread per stream, as pitchvis_train/src/train.rs:146-154 runs one Vqt per worker
+        sample = max(16, 2 * threads)
+        params, audio, hop, n_streams, fps_ = workload(args.workload, seed=0, rank=0, world=max(1, args.streams // sample),
                                                        n_streams_total=args.streams)
     else:
         params, audio, hop, n_streams, fps_ = workload(args.workload, seed=0)
     n_frames = n_streams * fps_
     rows = audio.reshape(n_streams, -1)
-    v = orc.OracleVqt(oracle_params(args.workload))
-    threads = host_threads()
+    if n_streams == 1:
+        v = orc.OracleVqt(oracle_params(args.workload))
 
-    def one_pass():
-        for r in rows:
-            v.calculate_batch_db(r, hop, fps_, mode=1, n_threads=threads)
+        def one_pass():
+            v.calculate_batch_db(rows[0], hop, fps_, mode=1, n_threads=threads)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        workers = [orc.OracleVqt(oracle_params(args.workload)) for _ in range(threads)]
+        pool = ThreadPoolExecutor(threads)
+
+        def work(w):   # the C call releases the GIL
+            for i in range(w, n_streams, threads):
+                workers[w].calculate_batch_db(rows[i], hop, fps_, mode=1, n_threads=1)
+
+        def one_pass():
+            list(pool.map(work, range(threads)))
 
     for _ in range(args.warmup):
         one_pass()
@@ -224,8 +237,10 @@ def run_reference(args, rank: int, world: int):
                               if args.workload != "streams4096" else
                               f"every step transforms the first {n_streams} streams ({n_frames} frames) of the workload")},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} passes over all {n_frames} frames of the workload, "
-                                   "oracle f32 path (C port of vqt.rs:866-954; the Rust crate cannot be built here)"},
+                         "sample": (f"{args.steps} passes over all {n_frames} frames of the workload, " if n_streams == 1
+                                    else f"{args.steps} passes over the first {n_streams} streams ({n_frames} frames), "
+                                         "one host thread per stream, ")
+                                   + "oracle f32 path (C port of vqt.rs:866-954; the Rust crate cannot be built here)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
