@@ -198,10 +198,10 @@ int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_lau
  * kept selectable).  A mode the kernel does not fit falls back to the next lower one.  Returns the mode in
  * effect. */
 int pvqt_set_fused_epilogue(pvqt *v, int mode);
-/* Plan introspection for tests and bench reports; out[0..n) (n <= 8): cluster size of K-spmm-db's cluster form
+/* Plan introspection for tests and bench reports; out[0..n) (n <= 9): cluster size of K-spmm-db's cluster form
  * (0: not available), co-resident clusters, shared-memory bytes of its coefficients, rows of its largest
  * part, warps of the one-CTA-per-tile form (0: not available), K-fft block size, columns per spectrum tile,
- * K-sdft plans cached. */
+ * K-sdft plans cached, band slots the warps of one K-spmm-db CTA walk per tile (padding included). */
 int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n);
 /* Test / tuning switch: 0 keeps every window group on the per-frame FFT path; 1 and 2 (default) let groups whose
  * consumed bins are cheaper as sums of hop-sized partial DFTs shared between overlapping frames take the K-sdft

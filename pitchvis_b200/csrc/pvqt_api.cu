@@ -1860,10 +1860,13 @@ int pvqt_set_fused_epilogue(pvqt *v, int mode)
 int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
 {
     if (!v || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
-    const int32_t info[8] = {v->cluster_capable ? v->cluster.cluster_size : 0, v->cluster_max_active, v->cluster.coef_bytes,
+    int32_t walk = 0;   // band slots the warps of one K-spmm-db CTA walk per tile (padding included)
+    if (v->fused_capable)
+        for (int w = 0; w < v->fused.n_warps; ++w) walk += v->fused.warp[w].width + v->fused.warp[w].nwidth;
+    const int32_t info[9] = {v->cluster_capable ? v->cluster.cluster_size : 0, v->cluster_max_active, v->cluster.coef_bytes,
                              v->cluster.max_rows, v->fused_capable ? v->fused.n_warps : 0, v->fft_block_threads,
-                             v->fft.spec_stride, (int32_t)v->sdft_plans.size()};
-    for (size_t i = 0; i < n && i < 8; ++i) out[i] = info[i];
+                             v->fft.spec_stride, (int32_t)v->sdft_plans.size(), walk};
+    for (size_t i = 0; i < n && i < 9; ++i) out[i] = info[i];
     return PVQT_OK;
 }
 

@@ -238,10 +238,10 @@ class Vqt:
         return int(self._lib.pvqt_set_fused_epilogue(self._h, int(mode)))
 
     def plan_info(self) -> dict:
-        out = (C.c_int32 * 8)()
-        _check(self._lib.pvqt_plan_info(self._h, out, 8))
+        out = (C.c_int32 * 9)()
+        _check(self._lib.pvqt_plan_info(self._h, out, 9))
         keys = ("cluster_size", "clusters_resident", "cluster_coef_bytes", "cluster_max_rows", "fused_warps",
-                "fft_block_threads", "spec_stride", "sdft_plans")
+                "fft_block_threads", "spec_stride", "sdft_plans", "fused_walk_slots")
         return dict(zip(keys, [int(x) for x in out]))
 
     def set_sliding_dft(self, mode) -> int:

@@ -462,6 +462,14 @@ def test_long_recording_crosses_launch_chunks(built_lib, oracle_default, monkeyp
     vqt.close(); whole.close()
 
 
+def test_spmm_plan_walk_slots(vqt):
+    """The K-spmm-db plan at the defaults: 294 units in 10 warps; keeping the units with a conjugate-part band in one
+    block holds the warps' walks to ~410 band slots per tile (sorting by len + nlen gave 435 + placement shifts)."""
+    info = vqt.plan_info()
+    assert info["fused_warps"] == 10
+    assert 380 <= info["fused_walk_slots"] <= 425, info
+
+
 def test_tile_flags_do_not_change_results(built_lib, vqt, chords, monkeypatch):
     """K-spmm-db starts a tile on the completion counts of K-sdft and of the K-fft CTAs that write it
     (PVQT_TILE_FLAGS=1) or on the whole K-fft grid (0): same bits, for a batch with a partial last tile, for short
