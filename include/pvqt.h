@@ -82,6 +82,14 @@ int         pvqt_abi_version(void);
 const char *pvqt_last_error_string(void);
 int         pvqt_device_count(int *count);
 
+/* Log sink.  The reference logs through the `log` crate: info! the analysis delay (vqt.rs:468), warn! a coverage gap
+ * between neighbouring filters' -3 dB bands (vqt.rs:695-710), debug! the structure of every window group and filter
+ * (vqt.rs:661-667, :688-694, :741-746, :843-846).  The sink receives the same lines from pvqt_kernel_create /
+ * pvqt_create; level: 1 = warn, 2 = info, 3 = debug; lines above max_level are not formatted.  fn == NULL removes
+ * the sink.  Process-wide, like the crate's global logger; the callback runs on the calling thread. */
+typedef void (*pvqt_log_fn)(int level, const char *message, void *user);
+int         pvqt_set_log_callback(pvqt_log_fn fn, void *user, int max_level);
+
 /* ---- parameters ------------------------------------------------------------- */
 /* `impl Default for VqtParameters` (vqt.rs:333-348, constants vqt.rs:180-214) */
 int pvqt_default_params(pvqt_params *out);
@@ -108,6 +116,13 @@ double pvqt_kernel_delay_seconds(const pvqt_kernel *k);
 size_t pvqt_kernel_num_window_groups(const pvqt_kernel *k);
 int    pvqt_kernel_group_window(const pvqt_kernel *k, size_t group, uint64_t *begin, uint64_t *end);
 int    pvqt_kernel_group_csr(const pvqt_kernel *k, size_t group, int negative, pvqt_csr_view *out);
+/* Diagnostic (Filter::bandwidth_3db_in_hz, vqt.rs:417-420, calculate_bandwidth vqt.rs:962-989): the -3 dB band of every
+ * filter in Hz, lo / hi: n == n_buckets entries each (either may be NULL). */
+int    pvqt_kernel_filter_bandwidths(const pvqt_kernel *k, float *lo_hz, float *hi_hz, size_t n);
+/* The filters below which the reference warns about a coverage gap (vqt.rs:695-710: the band of filter i starts above
+ * the end of the band of filter i - 1).  *count receives their number; up to `capacity` indices are stored in `out`
+ * (may be NULL).  None at the default parameters. */
+int    pvqt_kernel_coverage_gaps(const pvqt_kernel *k, uint32_t *out, size_t capacity, size_t *count);
 
 /* ---- construction (Vqt::new, vqt.rs:465-505) -------------------------------- */
 int  pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *err);

@@ -117,14 +117,42 @@ int  pvqt_chroma_device(const pvqt_range *range, int device, const float *d_db, 
  * crate: a display concern) and is passed in as bytes already scaled as update.rs:986-988 does,
  * bin_rgb[3 b + c] = (c * 255 * 1.2).clamp(0, 255) as u8.  n_frames frames at once: the image ends as if the
  * reference had processed them one by one (the last min(n_frames, height-1) frames own a row each, the row after
- * the last is cleared); *write_index is advanced by n_frames modulo height.  The Peaks mode of the same system
- * (update.rs:997-1062) colours by fractional bin and stays on the host.  Host and device-pointer forms; the device
+ * the last is cleared); *write_index is advanced by n_frames modulo height.  Host and device-pointer forms; the device
  * form with height 1 is the caller's memset. */
 int  pvqt_spectrogram_vqt(int device, const float *smoothed, size_t n_frames, size_t n_buckets, const uint8_t *bin_rgb,
                           uint8_t *image, size_t height, size_t *write_index);
 int  pvqt_spectrogram_vqt_device(int device, const float *d_smoothed, size_t n_frames, size_t n_buckets,
                                  const uint8_t *d_bin_rgb, uint8_t *d_image, size_t height, size_t *write_index,
                                  void *cuda_stream);
+
+/* SpectrogramMode::Peaks of the same system (update.rs:997-1062): a frame's row shows only its continuous peaks --
+ * every bin within PEAK_RADIUS = 2 bins of a peak centre gets the peak's pitch colour (pitchvis_colors::calculate_color
+ * of the FRACTIONAL bin, pitchvis_colors/src/lib.rs:93-119, computed here: it depends on the peak) and alpha =
+ * brightness(size / max size) * exp(-d^2 / 2); peaks are drawn in list order, later ones over earlier ones; all other
+ * pixels of the row keep the zeros the previous step left.  peaks / peak_count are exactly what K-analysis writes
+ * (pvqt_analysis_outputs::peaks_continuous [n_frames][max_peaks], ::peak_count [n_frames]), so the device form chains
+ * behind pvqt_analysis_preprocess_device without a host round trip.  width = range->octaves * buckets_per_octave. */
+int  pvqt_spectrogram_peaks(int device, const pvqt_range *range, const pvqt_continuous_peak *peaks, const uint32_t *peak_count,
+                            size_t max_peaks, size_t n_frames, uint8_t *image, size_t height, size_t *write_index);
+int  pvqt_spectrogram_peaks_device(int device, const pvqt_range *range, const pvqt_continuous_peak *d_peaks,
+                                   const uint32_t *d_peak_count, size_t max_peaks, size_t n_frames, uint8_t *d_image,
+                                   size_t height, size_t *write_index, void *cuda_stream);
+
+/* ---- VQT + AnalysisState in one call (BASELINE.json configs[4]) ----------------------------------------------
+ * Every caller of the reference runs the two back to back, per frame: Vqt::calculate_vqt_instant_in_db then
+ * AnalysisState::preprocess (pitchvis_viewer/src/vqt_system.rs:40-68 + analysis_system.rs:10-20;
+ * pitchvis_serial/src/main.rs:206-230).  These entries do it for whole recordings: host audio in (same layout and
+ * frame rule as pvqt_calc_batch_db / pvqt_calc_streams_db), the dB spectra go from the transform to K-analysis
+ * through HBM, and only the results `out` names travel back (host pointers, [S][T]... as in
+ * pvqt_analysis_preprocess_batch).  out_db (optional, may be NULL) also returns the spectra [S][T][NB].
+ * `a` must live on v's device, hold n_streams states and the same n_buckets; its states advance by
+ * frames_per_stream frames.  *d2h_bytes (optional) receives the bytes copied device -> host.  One recording must
+ * fit one staging batch (2^28 samples); more streams than fit are processed in groups. */
+int  pvqt_calc_batch_analysis(pvqt *v, pvqt_analysis *a, const float *audio, size_t n_samples, size_t hop, size_t n_frames,
+                              uint64_t frame_time_ns, const pvqt_analysis_outputs *out, float *out_db, uint64_t *d2h_bytes);
+int  pvqt_calc_streams_analysis(pvqt *v, pvqt_analysis *a, const float *audio, size_t n_streams, size_t stream_stride,
+                                size_t n_samples, size_t hop, size_t frames_per_stream, uint64_t frame_time_ns,
+                                const pvqt_analysis_outputs *out, float *out_db, uint64_t *d2h_bytes);
 
 #ifdef __cplusplus
 }

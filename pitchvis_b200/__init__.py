@@ -7,9 +7,9 @@ used by the tests and bench; the Rust shim crates (rust/) bind the same ABI.  Th
 from .vqt import (  # noqa: F401
     AboveNyquist, CsMat, DeviceBuffer, HostKernel, MultiVqt, PvqtRuntimeError, Vqt, VqtError, VqtKernel,
     VqtParameters, VqtRange, WindowExceedsNFft, WindowGroup, calc_db_device, fft_device, filter_bank_params,
-    synchronize,
+    set_log_callback, synchronize,
 )
 from .analysis import (  # noqa: F401,E402
-    AnalysisParameters, AnalysisState, PeakDetectionParameters, chroma, ml_input_windows, spectrogram_vqt,
+    AnalysisParameters, AnalysisState, PeakDetectionParameters, chroma, ml_input_windows, spectrogram_peaks, spectrogram_vqt,
 )
 from .agc import AgcError, MonoAgc  # noqa: F401,E402

@@ -123,6 +123,9 @@ SIGNATURES = {
     "pvqt_kernel_num_window_groups": (_SZ, [_VP]),
     "pvqt_kernel_group_window": (C.c_int, [_VP, _SZ, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pvqt_kernel_group_csr": (C.c_int, [_VP, _SZ, C.c_int, C.POINTER(PvqtCsrView)]),
+    "pvqt_kernel_filter_bandwidths": (C.c_int, [_VP, _FP, _FP, _SZ]),
+    "pvqt_kernel_coverage_gaps": (C.c_int, [_VP, C.POINTER(C.c_uint32), _SZ, C.POINTER(_SZ)]),
+    "pvqt_set_log_callback": (C.c_int, [_VP, _VP, C.c_int]),
     "pvqt_create": (C.c_int, [C.POINTER(PvqtParams), C.c_int, C.POINTER(_VP), C.POINTER(PvqtError)]),
     "pvqt_destroy": (None, [_VP]),
     "pvqt_get_params": (C.c_int, [_VP, C.POINTER(PvqtParams)]),
@@ -188,6 +191,14 @@ SIGNATURES = {
     "pvqt_spectrogram_vqt": (C.c_int, [C.c_int, _FP, _SZ, _SZ, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _SZ,
                                        C.POINTER(C.c_size_t)]),
     "pvqt_spectrogram_vqt_device": (C.c_int, [C.c_int, _VP, _SZ, _SZ, _VP, _VP, _SZ, C.POINTER(C.c_size_t), _VP]),
+    "pvqt_spectrogram_peaks": (C.c_int, [C.c_int, C.POINTER(PvqtRange), _VP, _VP, _SZ, _SZ, C.POINTER(C.c_uint8), _SZ,
+                                         C.POINTER(C.c_size_t)]),
+    "pvqt_spectrogram_peaks_device": (C.c_int, [C.c_int, C.POINTER(PvqtRange), _VP, _VP, _SZ, _SZ, _VP, _SZ,
+                                                C.POINTER(C.c_size_t), _VP]),
+    "pvqt_calc_batch_analysis": (C.c_int, [_VP, _VP, _FP, _SZ, _SZ, _SZ, C.c_uint64, C.POINTER(PvqtAnalysisOutputs), _FP,
+                                           C.POINTER(C.c_uint64)]),
+    "pvqt_calc_streams_analysis": (C.c_int, [_VP, _VP, _FP, _SZ, _SZ, _SZ, _SZ, _SZ, C.c_uint64,
+                                             C.POINTER(PvqtAnalysisOutputs), _FP, C.POINTER(C.c_uint64)]),
     # include/pvqt_agc.h
     "pvqt_agc_create": (C.c_int, [C.c_float, C.c_float, _SZ, C.c_int, C.POINTER(_VP)]),
     "pvqt_agc_destroy": (None, [_VP]),
@@ -198,6 +209,8 @@ SIGNATURES = {
     "pvqt_agc_process_device": (C.c_int, [_VP, _VP, _SZ, _SZ, _SZ, C.c_float, _VP]),
     "pvqt_agc_synchronize": (C.c_int, [_VP]),
 }
+
+LOG_FN = C.CFUNCTYPE(None, C.c_int, C.c_char_p, C.c_void_p)   # pvqt_log_fn
 
 _lib = None
 

@@ -99,15 +99,8 @@ class AnalysisState:
         _check(self._lib.pvqt_analysis_update_vqt_smoothing_duration(
             self._h, 0 if new_duration_ns is None else 1, new_duration_ns or 0))
 
-    def preprocess_batch(self, db: np.ndarray, frame_time_ns: int, max_peaks: int = 64,
-                         vectors: bool = True) -> Dict[str, np.ndarray]:
-        """db: [n_streams][T][n_buckets] (or [T][n_buckets] for one stream).  Returns per-frame results."""
-        db = np.ascontiguousarray(db, np.float32)
-        if db.ndim == 2:
-            db = db[None]
-        if db.ndim != 3 or db.shape[0] != self.n_streams:
-            raise ValueError("db must be [n_streams][n_frames][n_buckets]")
-        S, T, NB = db.shape
+    def _result_buffers(self, S: int, T: int, max_peaks: int, vectors):
+        NB = self.n_buckets
         res = {
             "peak_count": np.zeros((S, T), np.uint32),
             "peak_indices": np.zeros((S, T, max_peaks), np.uint32),
@@ -115,15 +108,66 @@ class AnalysisState:
             "smoothed_scene_calmness": np.zeros((S, T), np.float32),
             "smoothed_tuning_grid_inaccuracy": np.zeros((S, T), np.float32),
         }
-        if vectors:
-            for name in VECTOR_FIELDS:
-                res[name] = np.zeros((S, T, NB), np.float32)
+        names = VECTOR_FIELDS if vectors is True else (tuple(vectors) if vectors else ())
+        for name in names:
+            if name not in VECTOR_FIELDS:
+                raise ValueError(f"unknown result vector {name!r}")
+            res[name] = np.zeros((S, T, NB), np.float32)
         out = PvqtAnalysisOutputs()
         out.max_peaks = max_peaks
         for name, arr in res.items():
             setattr(out, name, arr.ctypes.data_as(C.c_void_p))
+        return res, out
+
+    @staticmethod
+    def _check_peak_capacity(res, max_peaks: int):
+        most = int(res["peak_count"].max()) if res["peak_count"].size else 0
+        if most > max_peaks:
+            raise ValueError(f"a frame has {most} peaks but max_peaks is {max_peaks}: the stored peak lists are "
+                             "truncated (the states have advanced); pass a larger max_peaks")
+
+    def preprocess_batch(self, db: np.ndarray, frame_time_ns: int, max_peaks: int = 64,
+                         vectors=True) -> Dict[str, np.ndarray]:
+        """db: [n_streams][T][n_buckets] (or [T][n_buckets] for one stream).  Returns per-frame results.
+        `vectors`: True = every per-bin result, False = none, or an iterable of names out of VECTOR_FIELDS."""
+        db = np.ascontiguousarray(db, np.float32)
+        if db.ndim == 2:
+            db = db[None]
+        if db.ndim != 3 or db.shape[0] != self.n_streams:
+            raise ValueError("db must be [n_streams][n_frames][n_buckets]")
+        S, T, NB = db.shape
+        res, out = self._result_buffers(S, T, max_peaks, vectors)
         _check(self._lib.pvqt_analysis_preprocess_batch(
             self._h, db.ctypes.data_as(C.POINTER(C.c_float)), NB, T, frame_time_ns, C.byref(out)))
+        self._check_peak_capacity(res, max_peaks)
+        return res
+
+    def calculate_and_preprocess(self, vqt, audio, hop: int, frame_time_ns: int, frames_per_stream: Optional[int] = None,
+                                 max_peaks: int = 64, vectors=False, return_db: bool = False) -> Dict[str, np.ndarray]:
+        """VQT + preprocess in one library call (pvqt_calc_streams_analysis, BASELINE configs[4]): host audio in
+        ([n_samples] for a single-stream state, else [n_streams][n_samples]), the spectra stay in HBM between the
+        transform and the analysis epilogue, only the results come back.  `res["d2h_bytes"]` is what was copied."""
+        a = np.ascontiguousarray(audio, np.float32)
+        if a.ndim == 1:
+            a = a[None]
+        if a.ndim != 2 or a.shape[0] != self.n_streams:
+            raise ValueError("audio must be [n_streams][n_samples]")
+        if int(hop) <= 0:
+            raise ValueError("hop must be positive")
+        S, n_samples = a.shape
+        if frames_per_stream is None:
+            frames_per_stream = vqt.frames_in(n_samples, hop)
+        T = int(frames_per_stream)
+        res, out = self._result_buffers(S, T, max_peaks, vectors)
+        db = np.empty((S, T, self.n_buckets), np.float32) if return_db else None
+        moved = C.c_uint64(0)
+        _check(self._lib.pvqt_calc_streams_analysis(
+            vqt.handle, self._h, a.ctypes.data_as(C.POINTER(C.c_float)), S, n_samples, n_samples, int(hop), T,
+            frame_time_ns, C.byref(out), db.ctypes.data_as(C.POINTER(C.c_float)) if return_db else None, C.byref(moved)))
+        self._check_peak_capacity(res, max_peaks)
+        if return_db:
+            res["db"] = db
+        res["d2h_bytes"] = int(moved.value)
         return res
 
     def preprocess(self, x_vqt, frame_time_ns: int) -> Dict[str, np.ndarray]:
@@ -135,7 +179,7 @@ class AnalysisState:
             raise ValueError("preprocess() is the single-stream entry; use preprocess_batch")
         if x.shape[0] != self.n_buckets:
             raise ValueError("x_vqt.len() must equal range.n_buckets()")
-        r = self.preprocess_batch(x[None, None, :], frame_time_ns)
+        r = self.preprocess_batch(x[None, None, :], frame_time_ns, max_peaks=min(256, self.n_buckets // 2 + 1))
         n = int(r["peak_count"][0, 0])
         out = {k: v[0, 0] for k, v in r.items()}
         out["peaks"] = set(int(i) for i in r["peak_indices"][0, 0, :n])
@@ -172,6 +216,27 @@ def spectrogram_vqt(smoothed: np.ndarray, bin_rgb: np.ndarray, image: np.ndarray
     u8 = C.POINTER(C.c_uint8)
     _check(_ffi.load().pvqt_spectrogram_vqt(device, x.ctypes.data_as(C.POINTER(C.c_float)), x.shape[0], x.shape[1],
                                             rgb.ctypes.data_as(u8), image.ctypes.data_as(u8), image.shape[0], C.byref(w)))
+    return int(w.value)
+
+
+def spectrogram_peaks(peaks_continuous: np.ndarray, peak_count: np.ndarray, image: np.ndarray, write_index: int,
+                      range: Optional[VqtRange] = None, device: int = 0) -> int:
+    """The viewer's spectrogram ring in Peaks mode (pitchvis_viewer/src/display_system/update.rs:997-1062) for all frames
+    at once.  `peaks_continuous` [frames][max_peaks][2] and `peak_count` [frames] are what `AnalysisState.preprocess_batch`
+    returns for one stream; `image` is the RGBA8 ring [height][n_buckets][4], updated in place.  Returns the new index."""
+    rng = range if range is not None else VqtRange()
+    pk = np.ascontiguousarray(peaks_continuous, np.float32)
+    cnt = np.ascontiguousarray(peak_count, np.uint32)
+    if pk.ndim != 3 or pk.shape[2] != 2 or cnt.shape != (pk.shape[0],):
+        raise ValueError("peaks_continuous must be [frames][max_peaks][2] and peak_count [frames]")
+    if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 4 or not image.flags.c_contiguous or \
+            image.shape[1] != rng.n_buckets():
+        raise ValueError("image must be a C-contiguous uint8 array [height][n_buckets][4]")
+    w = C.c_size_t(int(write_index))
+    r = PvqtRange(rng.min_freq, rng.octaves, rng.buckets_per_octave)
+    _check(_ffi.load().pvqt_spectrogram_peaks(device, C.byref(r), pk.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p),
+                                              pk.shape[1], pk.shape[0], image.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                              image.shape[0], C.byref(w)))
     return int(w.value)
 
 

@@ -10,6 +10,7 @@
 // truncated to whole milliseconds (analysis.rs:319), so rounding differences are kept to libm's
 // the rare last-bit differences of correctly rounded transcendentals (cr_* below).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -20,6 +21,7 @@
 
 #include "last_error.hpp"
 #include "pvqt_analysis.h"
+#include "pvqt_internal.hpp"
 
 namespace {
 
@@ -400,7 +402,38 @@ struct pvqt_analysis {
     int has_horizon = 1;
     cudaStream_t stream = nullptr;
     float *st_smoothed = nullptr, *st_calm = nullptr, *st_released = nullptr, *st_afterglow = nullptr, *st_scalar = nullptr;
+    // device mirrors of the result buffers of the single-call pipeline (pvqt_calc_*_analysis), reused across calls
+    static constexpr int kOutputs = 11;
+    void *mirror[kOutputs] = {};
+    size_t mirror_bytes[kOutputs] = {};
 };
+
+namespace {
+
+// the members of pvqt_analysis_outputs in declaration order, with their bytes per frame
+inline void *&out_member(pvqt_analysis_outputs &o, int i)
+{
+    void **m[pvqt_analysis::kOutputs] = {
+        reinterpret_cast<void **>(&o.peak_count), reinterpret_cast<void **>(&o.peak_indices),
+        reinterpret_cast<void **>(&o.peaks_continuous), reinterpret_cast<void **>(&o.x_vqt_smoothed),
+        reinterpret_cast<void **>(&o.x_vqt_peakfiltered), reinterpret_cast<void **>(&o.x_vqt_afterglow),
+        reinterpret_cast<void **>(&o.calmness), reinterpret_cast<void **>(&o.pitch_accuracy),
+        reinterpret_cast<void **>(&o.pitch_deviation), reinterpret_cast<void **>(&o.smoothed_scene_calmness),
+        reinterpret_cast<void **>(&o.smoothed_tuning_grid_inaccuracy)};
+    return *m[i];
+}
+inline size_t out_bytes_per_frame(int i, size_t nb, size_t max_peaks)
+{
+    switch (i) {
+    case 0: return sizeof(uint32_t);
+    case 1: return max_peaks * sizeof(uint32_t);
+    case 2: return max_peaks * sizeof(pvqt_continuous_peak);
+    case 9: case 10: return sizeof(float);
+    default: return nb * sizeof(float);
+    }
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -429,6 +462,13 @@ int pvqt_analysis_create(const pvqt_range *range, const pvqt_analysis_params *pa
     *out = nullptr;
     const size_t nb = (size_t)range->octaves * range->buckets_per_octave;
     if (nb < 3 || nb > 4096) return afail(PVQT_UNSUPPORTED, "n_buckets must be in [3, 4096]");
+    {   // peaks are strict local maxima at least max(2, min_distance) bins apart: the kernel keeps kMaxPeaksSmem of them
+        const float d = std::round((float)range->buckets_per_octave * 0.4f / 12.0f);   // peak_detection.rs:37
+        const size_t apart = std::max<size_t>(2, d > 0.0f ? (size_t)d : 0);
+        if ((nb + apart - 1) / apart > (size_t)kMaxPeaksSmem)
+            return afail(PVQT_UNSUPPORTED, "more than " + std::to_string(kMaxPeaksSmem) +
+                                               " peaks per frame are possible for this range (n_buckets / min_distance)");
+    }
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess) return acuda(e, "cudaGetDeviceCount (no CPU fallback exists)");
@@ -461,6 +501,7 @@ void pvqt_analysis_destroy(pvqt_analysis *a)
     cudaSetDevice(a->device);
     if (a->stream) { cudaStreamSynchronize(a->stream); cudaStreamDestroy(a->stream); }
     for (float *p : {a->st_smoothed, a->st_calm, a->st_released, a->st_afterglow, a->st_scalar}) cudaFree(p);
+    for (void *p : a->mirror) if (p) cudaFree(p);
     delete a;
 }
 
@@ -480,7 +521,21 @@ int pvqt_analysis_preprocess_device(pvqt_analysis *a, const float *d_db, size_t 
 {
     if (!a || !d_db) return afail(PVQT_INVALID_ARGUMENT, "null argument");
     if (n_buckets != a->nb) return afail(PVQT_BAD_LENGTH, "x_vqt.len() must equal range.n_buckets()");  // analysis.rs:289
-    if (n_frames == 0) return PVQT_OK;
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : a->stream;
+    return pvqt_detail::analysis_run_device(a, d_db, 0, a->n_streams, n_frames, frame_time_ns, d_out, 0, st);
+}
+
+}  // extern "C"
+
+int pvqt_detail::analysis_device(const pvqt_analysis *a) { return a ? a->device : -1; }
+
+int pvqt_detail::analysis_run_device(pvqt_analysis *a, const float *d_db, size_t first_stream, size_t n_streams,
+                                     size_t n_frames, uint64_t frame_time_ns, const pvqt_analysis_outputs *d_out,
+                                     size_t out_frame_offset, cudaStream_t st)
+{
+    if (!a || !d_db) return afail(PVQT_INVALID_ARGUMENT, "null argument");
+    if (first_stream + n_streams > a->n_streams) return afail(PVQT_INVALID_ARGUMENT, "stream range out of bounds");
+    if (n_frames == 0 || n_streams == 0) return PVQT_OK;
     if (n_frames > 0xffffffffull) return afail(PVQT_INVALID_ARGUMENT, "too many frames");
     ACUDA(cudaSetDevice(a->device));
     AnalysisKernelParams P{};
@@ -490,17 +545,68 @@ int pvqt_analysis_preprocess_device(pvqt_analysis *a, const float *d_db, size_t 
     P.bpo = (int32_t)a->range.buckets_per_octave;
     P.nb = (int32_t)a->nb;
     P.has_horizon = a->has_horizon;
-    P.st_smoothed = a->st_smoothed; P.st_calm = a->st_calm; P.st_released = a->st_released;
-    P.st_afterglow = a->st_afterglow; P.st_scalar = a->st_scalar;
+    const size_t so = first_stream * a->nb;
+    P.st_smoothed = a->st_smoothed + so; P.st_calm = a->st_calm + so; P.st_released = a->st_released + so;
+    P.st_afterglow = a->st_afterglow + so; P.st_scalar = a->st_scalar + 2 * first_stream;
     P.db = d_db;
     P.n_frames = (uint32_t)n_frames;
     P.frame_time_ns = frame_time_ns;
-    if (d_out) P.out = *d_out;
-    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : a->stream;
-    analysis_kernel<<<(unsigned)a->n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
+    if (d_out) {
+        P.out = *d_out;
+        for (int i = 0; i < pvqt_analysis::kOutputs && out_frame_offset != 0; ++i)
+            if (out_member(P.out, i))
+                out_member(P.out, i) = static_cast<char *>(out_member(P.out, i)) +
+                                       out_frame_offset * out_bytes_per_frame(i, a->nb, d_out->max_peaks);
+    }
+    analysis_kernel<<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
     ACUDA(cudaGetLastError());
     return PVQT_OK;
 }
+
+int pvqt_detail::analysis_outputs_reserve(pvqt_analysis *a, const pvqt_analysis_outputs *host, size_t frames,
+                                          pvqt_analysis_outputs *dev, cudaStream_t stream)
+{
+    *dev = pvqt_analysis_outputs{};
+    if (!host) return PVQT_OK;
+    ACUDA(cudaSetDevice(a->device));
+    dev->max_peaks = host->max_peaks;
+    pvqt_analysis_outputs h = *host;
+    for (int i = 0; i < pvqt_analysis::kOutputs; ++i) {
+        if (!out_member(h, i)) continue;
+        const size_t bytes = std::max<size_t>(frames * out_bytes_per_frame(i, a->nb, host->max_peaks), 16);
+        if (bytes > a->mirror_bytes[i]) {
+            if (a->mirror[i]) cudaFree(a->mirror[i]);
+            a->mirror[i] = nullptr;
+            a->mirror_bytes[i] = 0;
+            ACUDA(cudaMalloc(&a->mirror[i], bytes));
+            a->mirror_bytes[i] = bytes;
+        }
+        // slots past a frame's peak_count stay 0
+        if (i == 1 || i == 2) ACUDA(cudaMemsetAsync(a->mirror[i], 0, bytes, stream));
+        out_member(*dev, i) = a->mirror[i];
+    }
+    return PVQT_OK;
+}
+
+int pvqt_detail::analysis_outputs_download(pvqt_analysis *a, const pvqt_analysis_outputs *host,
+                                           const pvqt_analysis_outputs *dev, size_t frames, cudaStream_t stream,
+                                           size_t *bytes_out)
+{
+    size_t total = 0;
+    if (host) {
+        pvqt_analysis_outputs h = *host, d = *dev;
+        for (int i = 0; i < pvqt_analysis::kOutputs; ++i) {
+            if (!out_member(h, i) || !out_member(d, i)) continue;
+            const size_t bytes = frames * out_bytes_per_frame(i, a->nb, host->max_peaks);
+            ACUDA(cudaMemcpyAsync(out_member(h, i), out_member(d, i), bytes, cudaMemcpyDeviceToHost, stream));
+            total += bytes;
+        }
+    }
+    if (bytes_out) *bytes_out = total;
+    return PVQT_OK;
+}
+
+extern "C" {
 
 int pvqt_analysis_synchronize(pvqt_analysis *a)
 {

@@ -9,10 +9,32 @@
 #include "kernel_builder.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdarg>
+#include <cstdio>
 #include <cstring>
+#include <limits>
+#include <mutex>
 
 namespace pvqt_host {
+
+// ---- log sink (the `log` crate's global logger, as a C callback) ----------------------------------------
+namespace {
+std::mutex g_log_mutex;
+pvqt_log_fn g_log_fn = nullptr;
+void *g_log_user = nullptr;
+std::atomic<int> g_log_level{0};
+}  // namespace
+
+bool log_enabled(int level) { return level <= g_log_level.load(std::memory_order_relaxed); }
+
+void log_line(int level, const std::string &message)
+{
+    std::lock_guard<std::mutex> lock(g_log_mutex);
+    if (g_log_fn && level <= g_log_level.load(std::memory_order_relaxed)) g_log_fn(level, message.c_str(), g_log_user);
+}
+
 namespace {
 
 constexpr float  kPiF = 3.14159274101257324219f;  // std::f32::consts::PI
@@ -86,9 +108,36 @@ struct PanicMessage {
 };
 
 // Vqt::calculate_filter, vqt.rs:769-852.  `v` receives scaled_n_fft coefficients.
+// calculate_bandwidth + find_3db_points + util::arg_max (vqt.rs:956-989, util.rs:49-58): the -3 dB points of the
+// (decimated) frequency response, a crude diagnostic the reference computes for its coverage-gap warning
+void bandwidth_3db(const std::vector<float> &response, float scaled_sr, float &lo_hz, float &hi_hz)
+{
+    size_t center = 0;
+    float best = -std::numeric_limits<float>::max();          // fold from f32::MIN, strict >
+    for (size_t i = 0; i < response.size(); ++i)
+        if (response[i] > best) { best = response[i]; center = i; }
+    const float threshold = response[center] / std::sqrt(2.0f);
+    size_t lower = center, upper = center;
+    while (lower > 0 && response[lower] > threshold) --lower;
+    while (upper < response.size() - 1 && response[upper] > threshold) ++upper;
+    lo_hz = static_cast<float>(lower) * scaled_sr / static_cast<float>(response.size());
+    hi_hz = static_cast<float>(upper) * scaled_sr / static_cast<float>(response.size());
+}
+
+std::string fmt(const char *format, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, format);
+    std::vsnprintf(buf, sizeof(buf), format, ap);
+    va_end(ap);
+    return buf;
+}
+
 bool calculate_filter(float sr, float sparsity_quantile, uint64_t sr_scaling, const FilterParams &fp,
                       uint64_t win_begin, uint64_t win_end, float window_center, Dft64 &fft,
-                      std::vector<cf> &v, std::vector<cd> &work, std::vector<float> &mags, PanicMessage &panic)
+                      std::vector<cf> &v, std::vector<cd> &work, std::vector<float> &mags, PanicMessage &panic,
+                      float &band_lo_hz, float &band_hi_hz)
 {
     const float m = static_cast<float>(sr_scaling);
     const float scaled_freq = fp.freq * m;                                              // :778
@@ -140,6 +189,7 @@ bool calculate_filter(float sr, float sparsity_quantile, uint64_t sr_scaling, co
     // :813-842 -- drop the smallest coefficients carrying (1 - q) of the L1 mass
     mags.resize(scaled_n_fft);
     for (size_t i = 0; i < scaled_n_fft; ++i) mags[i] = std::hypot(v[i].real(), v[i].imag());
+    bandwidth_3db(mags, sr / m, band_lo_hz, band_hi_hz);                               // :818-819
     std::vector<float> &sorted = mags;
     std::sort(sorted.begin(), sorted.end());                                            // :823
     float v_abs_sum = 0.0f;
@@ -156,8 +206,12 @@ bool calculate_filter(float sr, float sparsity_quantile, uint64_t sr_scaling, co
         ++cutoff_idx;
     }
     const float cutoff_value = cutoff_idx == 0 ? 0.0f : sorted[cutoff_idx - 1];         // :831-835
+    size_t erased = 0;
     for (cf &z : v)                                                                     // :837-842
-        if (std::hypot(z.real(), z.imag()) < cutoff_value) z = cf(0.0f, 0.0f);
+        if (std::hypot(z.real(), z.imag()) < cutoff_value) { z = cf(0.0f, 0.0f); ++erased; }
+    if (log_enabled(kLogDebug))                                                         // :843-846
+        log_line(kLogDebug, fmt("for freq %g erased %zu points below %g with sum %g out of total %g", fp.freq, erased,
+                                cutoff_value, accum, v_abs_sum));
     return true;
 }
 
@@ -277,6 +331,9 @@ bool build_kernel(const pvqt_params &p, Kernel &out, BuildError &err)
 
     out = Kernel{};
     out.n_buckets = nb;
+    out.band_lo_hz.assign(nb, 0.0f);
+    out.band_hi_hz.assign(nb, 0.0f);
+    float last_upper_bandwidth = 0.0f;                                                // :650
     std::vector<cf> v;
     std::vector<cd> work;
     std::vector<float> mags;
@@ -292,6 +349,10 @@ bool build_kernel(const pvqt_params &p, Kernel &out, BuildError &err)
         wg.window_end = rate_groups[a].end;
         const uint64_t window_size = wg.window_size();                                // :657
         const size_t n_spectrum = static_cast<size_t>(window_size / 2 + 1);           // :658
+        if (log_enabled(kLogDebug))                                                   // :661-667
+            log_line(kLogDebug, fmt("window (%llu, %llu) (%llu samples): %zu filters in %zu rate group(s)",
+                                    (unsigned long long)wg.window_begin, (unsigned long long)wg.window_end,
+                                    (unsigned long long)window_size, n_filters, b - a));
         std::vector<Triplet> pos, neg;
         int32_t row = 0;
         for (size_t g = a; g < b; ++g) {
@@ -305,12 +366,30 @@ bool build_kernel(const pvqt_params &p, Kernel &out, BuildError &err)
             Dft64 fft(scaled_n_fft);                                                  // :675
             for (size_t f = 0; f < rg.count; ++f) {
                 PanicMessage panic{nullptr};
-                if (!calculate_filter(p.sr, p.sparsity_quantile, rg.factor, filters[rg.first + f], wg.window_begin,
-                                      wg.window_end, window_center, fft, v, work, mags, panic)) {
+                const FilterParams &fp = filters[rg.first + f];
+                float lo_hz = 0.0f, hi_hz = 0.0f;
+                if (!calculate_filter(p.sr, p.sparsity_quantile, rg.factor, fp, wg.window_begin,
+                                      wg.window_end, window_center, fft, v, work, mags, panic, lo_hz, hi_hz)) {
                     err.status = PVQT_PANIC;
                     err.message = panic.text ? panic.text : "panic in calculate_filter";
                     return false;
                 }
+                out.band_lo_hz[rg.first + f] = lo_hz;
+                out.band_hi_hz[rg.first + f] = hi_hz;
+                if (log_enabled(kLogDebug))                                           // :688-694
+                    log_line(kLogDebug, fmt("filter at %.1f Hz: window %.1f samples, -3 dB band (%.2f, %.2f) Hz", fp.freq,
+                                            fp.window_length, lo_hz, hi_hz));
+                if (last_upper_bandwidth > 0.0f && lo_hz > last_upper_bandwidth) {    // :695-710
+                    out.coverage_gaps.push_back(static_cast<uint32_t>(rg.first + f));
+                    if (log_enabled(kLogWarn))
+                        log_line(kLogWarn,
+                                 fmt("coverage gap below the filter at %.1f Hz: its -3 dB band starts at %.2f Hz but the "
+                                     "previous filter's band ends at %.2f Hz (%.1f%% of this filter's bandwidth); decrease "
+                                     "quality to close the gap",
+                                     fp.freq, lo_hz, last_upper_bandwidth,
+                                     100.0f * (lo_hz - last_upper_bandwidth) / (hi_hz - lo_hz)));
+                }
+                last_upper_bandwidth = hi_hz;                                         // :711
                 for (size_t j = 0; j < scaled_n_fft; ++j) {                           // :725-735
                     const cf z = v[j];
                     if (z.real() == 0.0f && z.imag() == 0.0f) continue;               // z.is_zero()
@@ -328,12 +407,27 @@ bool build_kernel(const pvqt_params &p, Kernel &out, BuildError &err)
         }
         to_csr(pos, static_cast<int32_t>(n_filters), static_cast<int32_t>(n_spectrum), wg.filter_bank);
         to_csr(neg, static_cast<int32_t>(n_filters), static_cast<int32_t>(n_spectrum), wg.negative_filter_bank);
+        if (log_enabled(kLogDebug))                                                   // :741-746
+            log_line(kLogDebug, fmt("window (%llu, %llu): kernel nnz %lld, conjugate-part nnz %lld",
+                                    (unsigned long long)wg.window_begin, (unsigned long long)wg.window_end,
+                                    (long long)wg.filter_bank.nnz(), (long long)wg.negative_filter_bank.nnz()));
         out.window_groups.push_back(std::move(wg));
         a = b;
     }
     // :756 Duration::from_secs_f32((n_fft as f32 - window_center) / sr)
     out.delay_seconds = static_cast<double>((static_cast<float>(p.n_fft) - window_center) / p.sr);
+    if (log_enabled(kLogInfo))                                                        // vqt.rs:468 (Vqt::new)
+        log_line(kLogInfo, fmt("VQT analysis delay: %llu ms.", (unsigned long long)(out.delay_seconds * 1000.0)));
     return true;
 }
 
 }  // namespace pvqt_host
+
+extern "C" int pvqt_set_log_callback(pvqt_log_fn fn, void *user, int max_level)
+{
+    std::lock_guard<std::mutex> lock(pvqt_host::g_log_mutex);
+    pvqt_host::g_log_fn = fn;
+    pvqt_host::g_log_user = user;
+    pvqt_host::g_log_level.store(fn ? std::max(0, std::min(max_level, 3)) : 0);
+    return PVQT_OK;
+}

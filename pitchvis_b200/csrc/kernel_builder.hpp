@@ -44,6 +44,10 @@ struct Kernel {
     std::vector<WindowGroup> window_groups;
     double delay_seconds = 0.0;
     size_t n_buckets = 0;
+    // diagnostic only (Filter::bandwidth_3db_in_hz, vqt.rs:417-420, :818-819): -3 dB band of every filter, and the
+    // filters below which the reference warns about a coverage gap (vqt.rs:695-710)
+    std::vector<float> band_lo_hz, band_hi_hz;
+    std::vector<uint32_t> coverage_gaps;
 };
 
 struct BuildError {
@@ -52,6 +56,14 @@ struct BuildError {
     uint64_t n_fft = 0;
     std::string message;
 };
+
+// The reference logs through the `log` crate: info! the delay (vqt.rs:468), warn! coverage gaps between neighbouring
+// filters' -3 dB bands (vqt.rs:695-710), debug! the structure of every window group and filter (vqt.rs:661-667,
+// :688-694, :741-746, :843-846).  A sink installed with pvqt_set_log_callback receives the same lines; messages of a
+// level the sink did not ask for are not even formatted.
+enum LogLevel { kLogWarn = 1, kLogInfo = 2, kLogDebug = 3 };
+bool log_enabled(int level);
+void log_line(int level, const std::string &message);
 
 // Vqt::filter_bank_params, vqt.rs:517-587
 bool filter_bank_params(const pvqt_params &p, std::vector<FilterParams> &out, BuildError &err);

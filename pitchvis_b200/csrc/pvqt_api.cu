@@ -21,6 +21,7 @@
 #include "kernel_builder.hpp"
 #include "last_error.hpp"
 #include "pvqt.h"
+#include "pvqt_internal.hpp"
 #include "vqt_device.cuh"
 
 using namespace pvqt_dev;
@@ -54,6 +55,24 @@ int cuda_fail(cudaError_t e, const char *what)
     } while (0)
 
 constexpr double kPi = 3.14159265358979323846;
+
+// a * b without wrapping: false if the product does not fit size_t
+bool mul_ok(size_t a, size_t b, size_t *out)
+{
+    if (a != 0 && b > SIZE_MAX / a) return false;
+    *out = a * b;
+    return true;
+}
+
+// (frames - 1) * hop + n_fft <= n_samples, evaluated without overflow (a huge hop or frame count must fail the
+// length check, not wrap past it)
+bool frames_fit(size_t frames, size_t hop, size_t n_fft, size_t n_samples)
+{
+    if (frames == 0) return true;
+    if (n_samples < n_fft) return false;
+    if (frames == 1 || hop == 0) return true;
+    return (n_samples - n_fft) / hop >= frames - 1;
+}
 
 // mirrors plan_radix() of vqt_kernels.cu (host copy used to size the twiddle tables)
 int host_plan_radix(int nc, int pass)
@@ -113,7 +132,8 @@ struct pvqt {
                    n_samples == o.n_samples && hop == o.hop && frames_per_stream == o.frames_per_stream &&
                    generations == o.generations;
         }
-    } graph_key;
+    } graph_key, graph_warm_key;   // warm: this call shape has run eagerly once (every plan built, every buffer reserved)
+    bool graph_warm = false;
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t graph_launches = 0;  // kernel launches one replay performs
     size_t segments_per_batch = 3;  // measured best on B200 + PCIe Gen5 (scripts/pcie_probe.py): 2-4 equal, 6+ slower
@@ -134,6 +154,7 @@ struct pvqt {
     std::vector<uint32_t> col_lo, n_cols, spec_off;
     size_t first_sample_used = 0;
     size_t last_sample_used = 0;        // one past
+    size_t upload_skip = 0;             // leading samples of a stream no kernel reads (multiple of 4: alignment is kept)
     uint32_t segment_cap = 16384;       // frames per copy/compute segment of the host-buffer entries (PVQT_SEGMENT_FRAMES)
     uint32_t chunk_frames = 131072;     // frames per launch (PVQT_CHUNK_FRAMES): measured 42.4 M frames/s at 8192, 46.7 M at
                                         // 131072 on 1024 streams x 511 frames (scripts/chunk_sweep.py); 850 MB of scratch
@@ -159,6 +180,13 @@ struct pvqt {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
         DeviceBuffer spec, power, sdft_c, sdft_r, tile_ready;
+        // The scratch above is reused by every launch chain of the lane.  Chains on one stream are ordered by the
+        // stream; when a chain is enqueued on another stream than the lane's previous one (a device-pointer entry
+        // on a caller stream after a host entry, two caller streams, ...) it first waits for `scratch_free`, which
+        // the previous chain recorded behind its last kernel.
+        cudaEvent_t scratch_free = nullptr;
+        cudaStream_t last_stream = nullptr;
+        bool used = false;
         unsigned *sdft_done = nullptr;   // completion counter of the lane's K-sdft launches (device, 4 bytes)
         uint32_t sdft_expected = 0;      // its value once every launch issued so far has finished
     } lane[kLanes];
@@ -169,6 +197,20 @@ struct pvqt {
     int n_lanes = 1;  // PVQT_LANES; measured on B200: 2 lanes -17 %, 3 lanes -29 % at 3507 frames
     DeviceBuffer d_audio, d_out;
     std::atomic<uint64_t> launches{0};
+    bool capturing = false;             // a stream capture is in progress: no cross-stream scratch events
+
+    // Per-frame entry (pvqt_calc_instant_db, the reference's real-time call at 60 FPS): persistent pinned staging,
+    // only the samples the windows read are uploaded, and the whole call -- H2D, K-fft, K-spmm-db, D2H -- is one
+    // captured graph; nothing is allocated and no event is created on the call path after the second call.
+    struct Instant {
+        float *h_in = nullptr, *h_out = nullptr;   // pinned
+        float *d_in = nullptr, *d_out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        uint64_t scratch_generation = 0;           // of lane[0].spec when `exec` was captured
+        int config = -1;                           // fused / sdft switches when `exec` was captured
+        uint64_t graph_launches = 0;
+        int calls = 0;
+    } instant;
 
     // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
     bool profiling = false;
@@ -220,6 +262,8 @@ int build_device_plan(pvqt *v)
         v->last_sample_used = std::max<size_t>(v->last_sample_used, g.window_end);
     }
     v->fft_block_threads = max_threads_per_fft <= 256 ? 256 : (max_threads_per_fft <= 512 ? 512 : 1024);
+    // K-fft transforms a window that begins on an odd sample one sample lower (vqt_kernels.cu, fft_group_body)
+    v->upload_skip = (v->first_sample_used > 0 ? v->first_sample_used - 1 : 0) & ~(size_t)3;
 
     // ---- FFT descriptors -------------------------------------------------------------
     FftParams &F = v->fft;
@@ -958,10 +1002,17 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                size_t frames_per_stream, float *d_out, float *d_power, float *d_spec_out, cudaStream_t stream,
                int scratch_lane = 0)
 {
-    const size_t total = n_streams * frames_per_stream;
-    if (total == 0) return PVQT_OK;
-    if (frames_per_stream > 0xffffffffull || n_streams > 0xffffffffull)
+    size_t total = 0;
+    if (frames_per_stream > 0x7fffffffull || n_streams > 0xffffffffull || !mul_ok(n_streams, frames_per_stream, &total))
         return fail(PVQT_INVALID_ARGUMENT, "too many frames per stream or streams");
+    if (total == 0) return PVQT_OK;
+    if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
+    {   // every sample offset a kernel forms must fit 64 bits with room to spare
+        size_t span = 0, all = 0;
+        if (!mul_ok(frames_per_stream - 1, hop, &span) || span > (SIZE_MAX >> 4) ||
+            (n_streams > 1 && (!mul_ok(n_streams, stream_stride, &all) || all > (SIZE_MAX >> 4))))
+            return fail(PVQT_INVALID_ARGUMENT, "hop / stream_stride too large");
+    }
     const size_t nb = v->kernel.n_buckets;
     const size_t chunk = v->chunk_frames;  // multiple of kTileFrames
     const size_t tile_elems = (size_t)v->fft.spec_stride * kTileFrames * 2;  // floats per tile
@@ -1018,6 +1069,16 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             const size_t s0 = ranges[ri].s0, ns = ranges[ri].ns, t0 = ranges[ri].t0, nf = ranges[ri].nf;
             pvqt::Lane &L = v->lane[use_lanes ? ri % (size_t)lanes : (size_t)scratch_lane];
             stream = use_lanes ? L.stream : caller_stream;
+            if (L.used && L.last_stream != stream && !v->use_graphs && !v->capturing)
+                PVQT_CUDA(cudaStreamWaitEvent(stream, L.scratch_free, 0));
+            struct ScratchRelease {   // records scratch_free behind the chain's last kernel, on every exit path
+                pvqt *v; pvqt::Lane &L; cudaStream_t s;
+                ~ScratchRelease()
+                {
+                    if (v->use_graphs || v->capturing) return;
+                    if (cudaEventRecord(L.scratch_free, s) == cudaSuccess) { L.last_stream = s; L.used = true; }
+                }
+            } scratch_release{v, L, stream};
             if (!d_spec_out) {
                 int rc = reserve_scratch(v, L, ns * nf, need_power, stream);
                 if (rc) return rc;
@@ -1062,7 +1123,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                     // completion counter for K-spmm-db's early combine; not under graph capture (the expected value
                     // would be baked into the graph) and not for the tcgen05 form
                     sp.done_counter = nullptr;
-                    if (v->tile_flags && !v->use_graphs && !on_tc && L.sdft_done != nullptr) {
+                    if (v->tile_flags && !v->use_graphs && !v->capturing && !on_tc && L.sdft_done != nullptr) {
                         sp.done_counter = L.sdft_done;
                         L.sdft_expected += sdft_partial_ctas(sp, v->sdft_tensor_cores);
                     } else {
@@ -1098,7 +1159,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             fp.n_groups = kept;
             fp.n_sdft = 0;
             // per-tile completion counts for K-spmm-db (one-CTA form only; not under graph capture; K-sdft must report too)
-            const bool flags = v->tile_flags && !v->use_graphs && v->fused_ok && !v->cluster_ok && !d_spec_out &&
+            const bool flags = v->tile_flags && !v->use_graphs && !v->capturing && v->fused_ok && !v->cluster_ok && !d_spec_out &&
                                kept > 0 && counted;
             fp.tile_ready = nullptr;
             if (flags) {
@@ -1288,7 +1349,8 @@ int compute_and_copy_out(pvqt *v, EventPool &ev, const HostJob &J, cudaEvent_t c
     PVQT_CUDA(ev.next(&done));
     PVQT_CUDA(cudaEventRecord(done, cs));
     PVQT_CUDA(cudaStreamWaitEvent(v->s_out, done, 0));
-    PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * J.nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
+    if (J.out != nullptr)   // nullptr: the dB spectra stay in HBM for the analysis epilogue (pvqt_calc_*_analysis)
+        PVQT_CUDA(cudaMemcpyAsync(h_out, d_out, ns * nf * J.nb * sizeof(float), cudaMemcpyDeviceToHost, v->s_out));
     return PVQT_OK;
 }
 
@@ -1299,9 +1361,18 @@ int enqueue_stream_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t b0, si
     const size_t per_seg = std::max<size_t>(1, segment_frames(v, nbatch * J.frames_per_stream) / J.frames_per_stream);
     for (size_t s0 = 0; s0 < nbatch; s0 += per_seg) {
         const size_t ns = std::min(per_seg, nbatch - s0);
-        PVQT_CUDA(cudaMemcpy2DAsync(d_audio + s0 * dstride, dstride * sizeof(float), J.audio + (b0 + s0) * J.stream_stride,
-                                    J.stream_stride * sizeof(float), J.span * sizeof(float), ns, cudaMemcpyHostToDevice,
-                                    v->s_in));
+        // samples before `skip` are never read by any kernel (the union of the windows starts later): not uploaded
+        const size_t skip = std::min(v->upload_skip, J.span);
+        const size_t max_pitch = (size_t)0x7fffffff;   // cudaDevAttrMaxPitch
+        if (ns > 1 && J.stream_stride * sizeof(float) <= max_pitch && dstride * sizeof(float) <= max_pitch) {
+            PVQT_CUDA(cudaMemcpy2DAsync(d_audio + s0 * dstride + skip, dstride * sizeof(float),
+                                        J.audio + (b0 + s0) * J.stream_stride + skip, J.stream_stride * sizeof(float),
+                                        (J.span - skip) * sizeof(float), ns, cudaMemcpyHostToDevice, v->s_in));
+        } else {
+            for (size_t s = 0; s < ns; ++s)
+                PVQT_CUDA(cudaMemcpyAsync(d_audio + (s0 + s) * dstride + skip, J.audio + (b0 + s0 + s) * J.stream_stride + skip,
+                                          (J.span - skip) * sizeof(float), cudaMemcpyHostToDevice, v->s_in));
+        }
         cudaEvent_t copied;
         PVQT_CUDA(ev.next(&copied));
         PVQT_CUDA(cudaEventRecord(copied, v->s_in));
@@ -1319,7 +1390,7 @@ int enqueue_frame_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t s, size
     float *d_audio = static_cast<float *>(v->d_audio.ptr), *d_out = static_cast<float *>(v->d_out.ptr);
     const float *h_audio = J.audio + s * J.stream_stride + b0 * J.hop;
     const size_t per_seg = segment_frames(v, nbatch);
-    size_t copied_samples = 0;
+    size_t copied_samples = std::min(v->upload_skip, (nbatch - 1) * J.hop + J.n_fft);   // never read: not uploaded
     for (size_t f0 = 0; f0 < nbatch; f0 += per_seg) {
         const size_t nf = std::min(per_seg, nbatch - f0);
         const size_t need = (f0 + nf - 1) * J.hop + J.n_fft;  // batch-relative end of this segment's samples
@@ -1338,16 +1409,25 @@ int enqueue_frame_batch(pvqt *v, EventPool &ev, const HostJob &J, size_t s, size
     return PVQT_OK;
 }
 
+// keep_on_device: `out` may be NULL (no D2H); the spectra of the call are left in v->d_out ([n_streams][frames][nb]),
+// complete once v->stream has drained -- the call then returns WITHOUT synchronising -- and the job must fit one
+// staging batch (PVQT_UNSUPPORTED otherwise; the caller splits by stream).
 int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples, size_t hop,
-             size_t frames_per_stream, float *out)
+             size_t frames_per_stream, float *out, bool keep_on_device = false)
 {
     HostJob J{audio, out, n_streams, stream_stride, n_samples, hop, frames_per_stream,
               (size_t)v->params.n_fft, v->kernel.n_buckets, 0};
     if (n_streams == 0 || frames_per_stream == 0) return PVQT_OK;
-    if (!audio || !out) return fail(PVQT_INVALID_ARGUMENT, "null buffer");
+    if (!audio || (!out && !keep_on_device)) return fail(PVQT_INVALID_ARGUMENT, "null buffer");
     if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
-    if (n_samples < J.n_fft || (frames_per_stream - 1) * hop + J.n_fft > n_samples)
+    if (!frames_fit(frames_per_stream, hop, J.n_fft, n_samples))
         return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
+    {
+        size_t t = 0;
+        if (frames_per_stream > 0x7fffffffull || n_streams > 0xffffffffull || !mul_ok(n_streams, frames_per_stream, &t) ||
+            !mul_ok(t, J.nb * sizeof(float), &t))
+            return fail(PVQT_INVALID_ARGUMENT, "too many frames per stream or streams");
+    }
     if (n_streams > 1 && stream_stride < n_samples)
         return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
     PVQT_CUDA(cudaSetDevice(v->device));
@@ -1362,6 +1442,7 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
     const bool single_batch = by_stream ? n_streams <= streams_per_batch
                                         : (n_streams == 1 && frames_per_stream <= frames_per_batch);
     EventPool ev{v};
+    if (keep_on_device && !single_batch) return fail(PVQT_UNSUPPORTED, "job exceeds one staging batch");
 
     if (single_batch) {
         const size_t audio_samples = by_stream ? n_streams * dstride : J.span;
@@ -1385,8 +1466,16 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         key.generations = v->d_audio.generation * 1000003u + v->d_out.generation * 10007u;
         for (const auto &L : v->lane)
             key.generations += L.spec.generation * 101u + L.power.generation + L.sdft_c.generation * 7u + L.sdft_r.generation * 13u;
-        if (v->use_graphs && !v->profiling) {
-            if (!(v->graph_exec && key == v->graph_key)) {
+        // A call shape is captured only after it has run eagerly with the same buffers: the first run builds the K-sdft
+        // plan of this hop and reserves every scratch buffer (cudaMalloc / cudaMemcpy are illegal under capture).
+        const bool replay = v->graph_exec && key == v->graph_key;
+        const bool warm = v->graph_warm && key == v->graph_warm_key;
+        if (v->use_graphs && !v->profiling && !keep_on_device && !replay && !warm) {
+            v->graph_warm_key = key;
+            v->graph_warm = true;
+        }
+        if (v->use_graphs && !v->profiling && !keep_on_device && (replay || warm)) {
+            if (!replay) {
                 if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 const uint64_t launches_before = v->launches.load();
@@ -1414,7 +1503,7 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         ev.used = 0;
         rc = enqueue();
         if (rc) return rc;
-        PVQT_CUDA(cudaStreamSynchronize(v->stream));
+        if (!keep_on_device) PVQT_CUDA(cudaStreamSynchronize(v->stream));
         return PVQT_OK;
     }
 
@@ -1445,6 +1534,80 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
                 PVQT_CUDA(cudaStreamSynchronize(v->stream));
             }
     }
+    return PVQT_OK;
+}
+
+// ---- per-frame entry: one captured graph -------------------------------------------------------
+void release_instant(pvqt *v)
+{
+    pvqt::Instant &I = v->instant;
+    if (I.exec) cudaGraphExecDestroy(I.exec);
+    if (I.h_in) cudaFreeHost(I.h_in);
+    if (I.h_out) cudaFreeHost(I.h_out);
+    if (I.d_in) cudaFree(I.d_in);
+    if (I.d_out) cudaFree(I.d_out);
+    I = pvqt::Instant{};
+}
+
+int run_instant(pvqt *v, const float *x, float *out)
+{
+    pvqt::Instant &I = v->instant;
+    const size_t n_fft = (size_t)v->params.n_fft, nb = v->kernel.n_buckets;
+    const size_t skip = std::min(v->upload_skip, n_fft), n_in = n_fft - skip;
+    PVQT_CUDA(cudaSetDevice(v->device));
+    if (!I.h_in) {
+        PVQT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&I.h_in), n_in * sizeof(float), cudaHostAllocDefault));
+        PVQT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&I.h_out), nb * sizeof(float), cudaHostAllocDefault));
+        PVQT_CUDA(cudaMalloc(reinterpret_cast<void **>(&I.d_in), n_fft * sizeof(float)));
+        PVQT_CUDA(cudaMalloc(reinterpret_cast<void **>(&I.d_out), nb * sizeof(float)));
+        PVQT_CUDA(cudaMemset(I.d_in, 0, n_fft * sizeof(float)));
+    }
+    std::memcpy(I.h_in, x + skip, n_in * sizeof(float));
+    auto enqueue = [&]() -> int {
+        PVQT_CUDA(cudaMemcpyAsync(I.d_in + skip, I.h_in, n_in * sizeof(float), cudaMemcpyHostToDevice, v->stream));
+        int rc = run_device(v, I.d_in, 1, 0, n_fft, 1, I.d_out, nullptr, nullptr, v->stream, 0);
+        if (rc) return rc;
+        PVQT_CUDA(cudaMemcpyAsync(I.h_out, I.d_out, nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
+        return PVQT_OK;
+    };
+    const int config = (v->fused_ok ? 1 : 0) | (v->cluster_ok ? 2 : 0);
+    if (I.exec && (I.scratch_generation != v->lane[0].spec.generation || I.config != config)) {
+        cudaGraphExecDestroy(I.exec);
+        I.exec = nullptr;
+        I.calls = 0;
+    }
+    // the first call runs eagerly (it reserves the lane's scratch: no allocation may happen under capture),
+    // the second is captured, every later one replays
+    if (!I.exec && I.calls >= 1 && !v->profiling) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = v->launches.load();
+        PVQT_CUDA(cudaStreamBeginCapture(v->stream, cudaStreamCaptureModeThreadLocal));
+        v->capturing = true;
+        int rc = enqueue();
+        v->capturing = false;
+        I.graph_launches = v->launches.load() - before;
+        v->launches.store(before);
+        cudaError_t e = cudaStreamEndCapture(v->stream, &graph);
+        if (rc == PVQT_OK && e == cudaSuccess && graph) {
+            e = cudaGraphInstantiate(&I.exec, graph, 0);
+            if (e != cudaSuccess) I.exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != PVQT_OK) { cudaGetLastError(); return rc; }
+        if (!I.exec) cudaGetLastError();   // capture unsupported here: stay eager
+        I.scratch_generation = v->lane[0].spec.generation;
+        I.config = config;
+    }
+    if (I.exec && !v->profiling) {
+        PVQT_CUDA(cudaGraphLaunch(I.exec, v->stream));
+        v->launches.fetch_add(I.graph_launches);
+    } else {
+        int rc = enqueue();
+        if (rc) return rc;
+    }
+    ++I.calls;
+    PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    std::memcpy(out, I.h_out, nb * sizeof(float));
     return PVQT_OK;
 }
 
@@ -1569,6 +1732,24 @@ int pvqt_kernel_group_csr(const pvqt_kernel *k, size_t group, int negative, pvqt
     return group_csr_of(k->kernel, group, negative, out);
 }
 
+int pvqt_kernel_filter_bandwidths(const pvqt_kernel *k, float *lo_hz, float *hi_hz, size_t n)
+{
+    if (!k) return fail(PVQT_INVALID_ARGUMENT, "null kernel");
+    if (n != k->kernel.n_buckets) return fail(PVQT_BAD_LENGTH, "lo / hi must hold n_buckets entries");
+    if (lo_hz) std::copy(k->kernel.band_lo_hz.begin(), k->kernel.band_lo_hz.end(), lo_hz);
+    if (hi_hz) std::copy(k->kernel.band_hi_hz.begin(), k->kernel.band_hi_hz.end(), hi_hz);
+    return PVQT_OK;
+}
+
+int pvqt_kernel_coverage_gaps(const pvqt_kernel *k, uint32_t *out, size_t capacity, size_t *count)
+{
+    if (!k || !count) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    *count = k->kernel.coverage_gaps.size();
+    if (out)
+        for (size_t i = 0; i < std::min(capacity, k->kernel.coverage_gaps.size()); ++i) out[i] = k->kernel.coverage_gaps[i];
+    return PVQT_OK;
+}
+
 int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *err)
 {
     pvqt_error local{};
@@ -1604,7 +1785,8 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
 
     for (auto &L : v->lane) {
         if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
+            (e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&L.scratch_free, cudaEventDisableTiming)) != cudaSuccess)
             return cuda_error(e, "create launch lanes");
         if ((e = cudaMalloc(&L.sdft_done, sizeof(unsigned))) != cudaSuccess ||
             (e = cudaMemset(L.sdft_done, 0, sizeof(unsigned))) != cudaSuccess)
@@ -1648,9 +1830,11 @@ void pvqt_destroy(pvqt *v)
         if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         if (L.done) cudaEventDestroy(L.done);
         if (L.sdft_done) cudaFree(L.sdft_done);
-        L.spec.release(); L.power.release(); L.sdft_c.release(); L.sdft_r.release();
+        L.spec.release(); L.power.release(); L.sdft_c.release(); L.sdft_r.release(); L.tile_ready.release();
+        if (L.scratch_free) cudaEventDestroy(L.scratch_free);
     }
     if (v->lane_fork) cudaEventDestroy(v->lane_fork);
+    release_instant(v);
     v->d_audio.release();
     v->d_out.release();
     delete v;
@@ -1703,7 +1887,7 @@ int pvqt_calc_instant_db(pvqt *v, const float *x, size_t n, float *out)
 {
     if (!v || !x || !out) return fail(PVQT_INVALID_ARGUMENT, "null argument");
     if (n != v->params.n_fft) return fail(PVQT_BAD_LENGTH, "input must be exactly n_fft samples");  // vqt.rs:867-871
-    return run_host(v, x, 1, 0, n, (size_t)v->params.n_fft, 1, out);
+    return run_instant(v, x, out);
 }
 
 int pvqt_calc_batch_db(pvqt *v, const float *audio, size_t n_samples, size_t hop, size_t n_frames, float *out)
@@ -1716,7 +1900,9 @@ int pvqt_calc_frames_db(pvqt *v, const float *frames, size_t n_frames, float *ou
 {
     if (!v) return fail(PVQT_INVALID_ARGUMENT, "null handle");
     const size_t n_fft = (size_t)v->params.n_fft;
-    return run_host(v, frames, 1, 0, n_frames * n_fft, n_fft, n_frames, out);
+    size_t n_samples = 0;
+    if (!mul_ok(n_frames, n_fft, &n_samples)) return fail(PVQT_INVALID_ARGUMENT, "too many frames");
+    return run_host(v, frames, 1, 0, n_samples, n_fft, n_frames, out);
 }
 
 int pvqt_calc_streams_db(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride, size_t n_samples,
@@ -1742,6 +1928,68 @@ int pvqt_fft_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stre
     PVQT_CUDA(cudaSetDevice(v->device));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : v->stream;
     return run_device(v, d_audio, n_streams, stream_stride, hop, frames_per_stream, nullptr, nullptr, d_spec, st);
+}
+
+// ---- VQT + AnalysisState in one call (BASELINE configs[4]) ------------------------------------
+// What every caller of the reference does per frame -- calculate_vqt_instant_in_db then preprocess
+// (pitchvis_viewer/src/vqt_system.rs:40-68 + analysis_system.rs:10-20, pitchvis_serial/src/main.rs:206-230) -- for
+// whole recordings: the dB spectra go from K-spmm-db to K-analysis through HBM and never visit the host unless
+// out_db asks for them.
+int pvqt_calc_streams_analysis(pvqt *v, pvqt_analysis *a, const float *audio, size_t n_streams, size_t stream_stride,
+                               size_t n_samples, size_t hop, size_t frames_per_stream, uint64_t frame_time_ns,
+                               const pvqt_analysis_outputs *out, float *out_db, uint64_t *d2h_bytes)
+{
+    if (!v || !a || !audio) return fail(PVQT_INVALID_ARGUMENT, "null argument");
+    if (pvqt_detail::analysis_device(a) != v->device)
+        return fail(PVQT_INVALID_ARGUMENT, "the Vqt and the AnalysisState must live on the same device");
+    const size_t nb = v->kernel.n_buckets, n_fft = (size_t)v->params.n_fft;
+    if (pvqt_analysis_n_buckets(a) != nb)
+        return fail(PVQT_BAD_LENGTH, "x_vqt.len() must equal range.n_buckets()");   // analysis.rs:289
+    if (pvqt_analysis_n_streams(a) != n_streams)
+        return fail(PVQT_INVALID_ARGUMENT, "the AnalysisState holds another number of streams");
+    if (d2h_bytes) *d2h_bytes = 0;
+    if (n_streams == 0 || frames_per_stream == 0) return PVQT_OK;
+    if (hop == 0 && frames_per_stream > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
+    if (!frames_fit(frames_per_stream, hop, n_fft, n_samples))
+        return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
+    size_t frames = 0;
+    if (!mul_ok(n_streams, frames_per_stream, &frames)) return fail(PVQT_INVALID_ARGUMENT, "too many frames");
+    PVQT_CUDA(cudaSetDevice(v->device));
+    pvqt_analysis_outputs dev{};
+    int rc = pvqt_detail::analysis_outputs_reserve(a, out, frames, &dev, v->stream);
+    if (rc) return rc;
+    // stream groups that fit one staging batch (one long recording must fit it as a whole)
+    const size_t span = (frames_per_stream - 1) * hop + n_fft, dstride = (span + 3) & ~(size_t)3;
+    const size_t group = std::max<size_t>(1, v->staging_budget_samples / dstride);
+    size_t total_d2h = 0;
+    for (size_t g0 = 0; g0 < n_streams; g0 += group) {
+        const size_t ng = std::min(group, n_streams - g0);
+        rc = run_host(v, audio + g0 * stream_stride, ng, stream_stride, n_samples, hop, frames_per_stream, nullptr, true);
+        if (rc) return rc;
+        const float *d_db = static_cast<const float *>(v->d_out.ptr);
+        rc = pvqt_detail::analysis_run_device(a, d_db, g0, ng, frames_per_stream, frame_time_ns, out ? &dev : nullptr,
+                                              g0 * frames_per_stream, v->stream);
+        if (rc) return rc;
+        v->launches.fetch_add(1);
+        if (out_db) {
+            const size_t bytes = ng * frames_per_stream * nb * sizeof(float);
+            PVQT_CUDA(cudaMemcpyAsync(out_db + g0 * frames_per_stream * nb, d_db, bytes, cudaMemcpyDeviceToHost, v->stream));
+            total_d2h += bytes;
+        }
+        if (g0 + group < n_streams) PVQT_CUDA(cudaStreamSynchronize(v->stream));   // d_audio / d_out are reused
+    }
+    size_t res_bytes = 0;
+    rc = pvqt_detail::analysis_outputs_download(a, out, &dev, frames, v->stream, &res_bytes);
+    if (rc) return rc;
+    PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    if (d2h_bytes) *d2h_bytes = total_d2h + res_bytes;
+    return PVQT_OK;
+}
+
+int pvqt_calc_batch_analysis(pvqt *v, pvqt_analysis *a, const float *audio, size_t n_samples, size_t hop, size_t n_frames,
+                             uint64_t frame_time_ns, const pvqt_analysis_outputs *out, float *out_db, uint64_t *d2h_bytes)
+{
+    return pvqt_calc_streams_analysis(v, a, audio, 1, 0, n_samples, hop, n_frames, frame_time_ns, out, out_db, d2h_bytes);
 }
 
 // ---- memory / timing helpers ---------------------------------------------------------------
@@ -2000,7 +2248,8 @@ int pvqt_multi_calc_batch_db(pvqt_multi *m, const float *audio, size_t n_samples
     if (!m || m->handles.empty()) return fail(PVQT_INVALID_ARGUMENT, "null handle");
     const size_t n_fft = pvqt_n_fft(m->handles[0]), nb = pvqt_n_buckets(m->handles[0]);
     if (n_frames == 0) return PVQT_OK;
-    if (n_samples < n_fft || (n_frames - 1) * hop + n_fft > n_samples)
+    if (hop == 0 && n_frames > 1) return fail(PVQT_INVALID_ARGUMENT, "hop must be positive");
+    if (!frames_fit(n_frames, hop, n_fft, n_samples))
         return fail(PVQT_BAD_LENGTH, "audio must hold (n_frames - 1) * hop + n_fft samples");
     return for_each_device(m, [&](size_t i) {
         size_t f0, f1, s0, s1;

@@ -302,8 +302,12 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
     // aligned) and undo the shift on the consumed bins in the split step:
     //   X[k] = W^-k (X'[k] + x[w + N - 1] - x[w - 1]),   W = exp(-2 pi i / N)
     // (exact algebra: the two windows differ by one sample at either end, and W^(N k) = 1).
+    // Which form a frame takes is a property of the window group alone (the parity of window_begin inside the frame),
+    // never of the address: the same n_fft samples give the same bits through every entry point, at every hop, in
+    // every shard.  The address only selects the load width of the first pass (8-byte loads when x - shifted is
+    // 8-byte aligned -- every frame at even hops and strides -- else two 4-byte loads of the same values).
 #ifndef PVQT_FFT_NO_SHIFT
-    const bool shifted = (reinterpret_cast<uintptr_t>(x) & 7) != 0 && g.window_begin >= 1;
+    const bool shifted = (g.window_begin & 1) != 0;
 #else
     const bool shifted = false;
 #endif

@@ -151,6 +151,23 @@ def _as_f32(a, name: str) -> np.ndarray:
     return a
 
 
+def _check_out(out: Optional[np.ndarray], shape) -> np.ndarray:
+    """A caller-supplied result buffer goes to the library as a raw pointer: it must be exactly what gets written."""
+    if out is None:
+        return np.empty(shape, np.float32)
+    if not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or \
+            tuple(out.shape) != tuple(shape):
+        raise ValueError(f"out must be a C-contiguous float32 array of shape {tuple(shape)}")
+    return out
+
+
+def _check_hop(hop) -> int:
+    hop = int(hop)
+    if hop <= 0:
+        raise ValueError("hop must be positive")
+    return hop
+
+
 def _csmat(view: PvqtCsrView) -> CsMat:
     nnz = int(view.nnz)
     indptr = np.ctypeslib.as_array(view.indptr, shape=(view.rows + 1,)).copy()
@@ -254,6 +271,8 @@ class Vqt:
     # ---- per-frame entry point (vqt.rs:866) ----------------------------------------------
     def calculate_vqt_instant_in_db(self, x) -> np.ndarray:
         x = _as_f32(x, "x")
+        if x.ndim != 1:
+            raise ValueError("input must be exactly n_fft samples")
         out = np.empty(self.n_buckets, np.float32)
         _check(self._lib.pvqt_calc_instant_db(self._h, _fptr(x), x.shape[0], _fptr(out)))
         return out
@@ -266,10 +285,12 @@ class Vqt:
                                   out: Optional[np.ndarray] = None) -> np.ndarray:
         """frame t = audio[t*hop : t*hop + n_fft]"""
         audio = _as_f32(audio, "audio")
+        if audio.ndim != 1:
+            raise ValueError("audio must be one recording [n_samples] (use calculate_vqt_streams_in_db for several)")
+        hop = _check_hop(hop)
         if n_frames is None:
             n_frames = self.frames_in(audio.shape[0], hop)
-        if out is None:
-            out = np.empty((n_frames, self.n_buckets), np.float32)
+        out = _check_out(out, (int(n_frames), self.n_buckets))
         _check(self._lib.pvqt_calc_batch_db(self._h, _fptr(audio), audio.shape[0], hop, n_frames, _fptr(out)))
         return out
 
@@ -288,10 +309,10 @@ class Vqt:
         if audio.ndim != 2:
             raise ValueError("audio must be [n_streams][n_samples]")
         n_streams, n_samples = audio.shape
+        hop = _check_hop(hop)
         if frames_per_stream is None:
             frames_per_stream = self.frames_in(n_samples, hop)
-        if out is None:
-            out = np.empty((n_streams, frames_per_stream, self.n_buckets), np.float32)
+        out = _check_out(out, (n_streams, int(frames_per_stream), self.n_buckets))
         _check(self._lib.pvqt_calc_streams_db(self._h, _fptr(audio), n_streams, n_samples, n_samples, hop,
                                               frames_per_stream, _fptr(out)))
         return out
@@ -388,6 +409,9 @@ class MultiVqt:
 
     def calculate_vqt_batch_in_db(self, audio, hop: int, n_frames: Optional[int] = None) -> np.ndarray:
         audio = _as_f32(audio, "audio")
+        if audio.ndim != 1:
+            raise ValueError("audio must be one recording [n_samples]")
+        hop = _check_hop(hop)
         if n_frames is None:
             n_frames = (audio.shape[0] - self.n_fft) // hop + 1 if audio.shape[0] >= self.n_fft else 0
         out = np.empty((n_frames, self.n_buckets), np.float32)
@@ -396,7 +420,10 @@ class MultiVqt:
 
     def calculate_vqt_streams_in_db(self, audio, hop: int, frames_per_stream: Optional[int] = None) -> np.ndarray:
         audio = _as_f32(audio, "audio")
+        if audio.ndim != 2:
+            raise ValueError("audio must be [n_streams][n_samples]")
         n_streams, n_samples = audio.shape
+        hop = _check_hop(hop)
         if frames_per_stream is None:
             frames_per_stream = (n_samples - self.n_fft) // hop + 1 if n_samples >= self.n_fft else 0
         out = np.empty((n_streams, frames_per_stream, self.n_buckets), np.float32)
@@ -449,6 +476,20 @@ class HostKernel:
         except Exception:
             pass
 
+    def filter_bandwidths(self):
+        """(-3 dB band start, end) in Hz of every filter: the reference's calculate_bandwidth diagnostic (vqt.rs:962-989)."""
+        lo, hi = np.empty(self.n_buckets, np.float32), np.empty(self.n_buckets, np.float32)
+        _check(self._lib.pvqt_kernel_filter_bandwidths(self._h, _fptr(lo), _fptr(hi), self.n_buckets))
+        return lo, hi
+
+    def coverage_gaps(self) -> List[int]:
+        """Filters below which the reference warns about a coverage gap (vqt.rs:695-710)."""
+        n = C.c_size_t(0)
+        _check(self._lib.pvqt_kernel_coverage_gaps(self._h, None, 0, C.byref(n)))
+        out = (C.c_uint32 * max(1, n.value))()
+        _check(self._lib.pvqt_kernel_coverage_gaps(self._h, out, n.value, C.byref(n)))
+        return [int(out[i]) for i in range(n.value)]
+
     def kernel(self) -> VqtKernel:
         groups = []
         for g in range(int(self._lib.pvqt_kernel_num_window_groups(self._h))):
@@ -459,3 +500,19 @@ class HostKernel:
             _check(self._lib.pvqt_kernel_group_csr(self._h, g, 1, C.byref(neg)))
             groups.append(WindowGroup((int(b.value), int(e.value)), _csmat(pos), _csmat(neg) if neg.nnz > 0 else None))
         return VqtKernel(groups)
+
+
+_log_keepalive = []
+
+
+def set_log_callback(fn, max_level: int = 2):
+    """Install `fn(level, message)` as the library's log sink (1 = warn, 2 = info, 3 = debug), or None to remove it.
+    Mirrors the `log` crate lines of the reference: delay (info), coverage gaps (warn), kernel structure (debug)."""
+    lib = _ffi.load()
+    if fn is None:
+        lib.pvqt_set_log_callback(None, None, 0)
+        _log_keepalive.clear()
+        return
+    cb = _ffi.LOG_FN(lambda level, msg, _user: fn(int(level), msg.decode("utf-8", "replace")))
+    _log_keepalive[:] = [cb]
+    lib.pvqt_set_log_callback(C.cast(cb, C.c_void_p), None, int(max_level))

@@ -473,3 +473,33 @@ def spectrogram_vqt(smoothed: np.ndarray, bin_rgb: np.ndarray, image: np.ndarray
         L.orc_spectrogram_vqt_step(_fptr(x[t]), x.shape[1], rgb.ctypes.data_as(u8), image.ctypes.data_as(u8), image.shape[0],
                                    C.byref(w))
     return int(w.value)
+
+
+def calculate_color(buckets_per_octave: int, bucket: float) -> np.ndarray:
+    """oracle/spectrogram_oracle.c: pitchvis_colors::calculate_color with the crate's COLORS / GRAY_LEVEL / EASING_POW."""
+    L = lib()
+    L.orc_calculate_color.argtypes = [C.c_uint32, C.c_float, C.POINTER(C.c_float)]
+    L.orc_calculate_color.restype = None
+    out = np.empty(3, np.float32)
+    L.orc_calculate_color(buckets_per_octave, bucket, _fptr(out))
+    return out
+
+
+def spectrogram_peaks(peaks_continuous: np.ndarray, peak_count: np.ndarray, image: np.ndarray, write_index: int,
+                      buckets_per_octave: int = 84) -> int:
+    """oracle/spectrogram_oracle.c: the spectrogram ring in Peaks mode, one update_spectrogram_system call per frame
+    (update.rs:997-1062).  peaks_continuous [frames][max_peaks][2], peak_count [frames]."""
+    L = lib()
+    u8 = C.POINTER(C.c_uint8)
+    L.orc_spectrogram_peaks_step.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_uint32, C.c_size_t, u8, C.c_size_t,
+                                             C.POINTER(C.c_size_t)]
+    L.orc_spectrogram_peaks_step.restype = None
+    pk = np.ascontiguousarray(peaks_continuous, np.float32)
+    assert image.dtype == np.uint8 and image.flags.c_contiguous and image.shape[2] == 4
+    w = C.c_size_t(write_index)
+    for t in range(pk.shape[0]):
+        n = min(int(peak_count[t]), pk.shape[1])
+        row = np.ascontiguousarray(pk[t, :n])
+        L.orc_spectrogram_peaks_step(_fptr(row) if n else None, n, buckets_per_octave, image.shape[1],
+                                     image.ctypes.data_as(u8), image.shape[0], C.byref(w))
+    return int(w.value)

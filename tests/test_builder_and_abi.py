@@ -133,3 +133,65 @@ def test_shard_range_and_halo(built_lib):
     assert (s0.value, s1.value) == (100 * 368, 199 * 368 + 32768)
     assert lib.pvqt_frame_range_samples(32768, 368, 5, 5, C.byref(s0), C.byref(s1)) == 0
     assert (s0.value, s1.value) == (0, 0)
+
+
+def test_log_callback_and_coverage_gap_diagnostic(built_lib):
+    # the reference's `log` lines (vqt.rs:468, :661-667, :688-710, :741-746) through pvqt_set_log_callback, and
+    # calculate_bandwidth's -3 dB bands (vqt.rs:962-989)
+    lines = []
+    pv.set_log_callback(lambda level, msg: lines.append((level, msg)), 3)
+    try:
+        k = pv.HostKernel(pv.VqtParameters.default())
+    finally:
+        pv.set_log_callback(None)
+    assert (2, "VQT analysis delay: 98 ms.") in lines
+    dbg = [m for lv, m in lines if lv == 3]
+    assert "window (24576, 32768) (8192 samples): 122 filters in 2 rate group(s)" in dbg
+    assert "window (24576, 32768): kernel nnz 3742, conjugate-part nnz 369" in dbg
+    assert "window (30087, 31111): kernel nnz 1578, conjugate-part nnz 0" in dbg
+    assert sum(m.startswith("filter at ") for m in dbg) == 588
+    assert not [m for lv, m in lines if lv == 1] and k.coverage_gaps() == []      # no gap at the defaults
+    lo, hi = k.filter_bandwidths()
+    fps = pv.filter_bank_params(pv.VqtParameters.default())
+    f = np.array([p[0] for p in fps])
+    assert np.all(lo < f) and np.all(f < hi) and np.all(hi - lo < 0.35 * f)
+    # a sharper bank leaves gaps between neighbouring -3 dB bands: the reference warns, so does the sink
+    warns = []
+    pv.set_log_callback(lambda level, msg: warns.append((level, msg)), 1)
+    try:
+        k2 = pv.HostKernel(pv.VqtParameters(quality=3.2, n_fft=65536))
+    finally:
+        pv.set_log_callback(None)
+    gaps = k2.coverage_gaps()
+    assert gaps and len(warns) == len(gaps) and all(lv == 1 and m.startswith("coverage gap below the filter at") for lv, m in warns)
+    n_before = len(warns)
+    pv.HostKernel(pv.VqtParameters(quality=3.2, n_fft=65536))                        # sink removed: silent
+    assert len(warns) == n_before
+
+
+def test_wrapper_argument_validation(built_lib):
+    # a caller-supplied result buffer goes to the library as a raw pointer: wrong dtype / shape / layout is refused
+    # before any pointer is formed (no GPU needed: the checks run first)
+    class _Stub(pv.Vqt):
+        def __init__(self):
+            self.n_buckets, self.n_fft = 588, 32768
+
+        def frames_in(self, n, hop):
+            return (n - self.n_fft) // hop + 1 if n >= self.n_fft else 0
+
+        def close(self):
+            pass
+
+    v = _Stub()
+    audio = np.zeros(32768 + 368, np.float32)
+    for bad in (np.zeros((2, 588), np.float64), np.zeros((3, 588), np.float32), np.zeros((2, 1176), np.float32)[:, ::2]):
+        with pytest.raises(ValueError):
+            v.calculate_vqt_batch_in_db(audio, 368, out=bad)
+    with pytest.raises(ValueError):
+        v.calculate_vqt_batch_in_db(audio, 0)
+    with pytest.raises(ValueError):
+        v.calculate_vqt_batch_in_db(audio, -368)
+    with pytest.raises(ValueError):
+        v.calculate_vqt_batch_in_db(np.zeros((2, 40000), np.float32), 368)
+    with pytest.raises(ValueError):
+        v.calculate_vqt_streams_in_db(np.zeros((2, 40000), np.float32), 368, out=np.zeros((2, 20, 587), np.float32))

@@ -182,3 +182,73 @@ def test_config5_full_recording(vqt, oracle_default):
             prom = scipy.signal.peak_prominences(sm, [q])[0][0]
             margins += [abs(prom - cfg[0]), abs(sm[q] - cfg[1])]
         assert margins and min(margins) < 5e-3, f"frame {t} bin {p}: not a near-tie (margins {margins})"
+
+
+def test_single_call_pipeline_matches_two_calls(vqt):
+    """pvqt_calc_batch_analysis (BASELINE configs[4] as one library call): the spectra stay in HBM between the transform
+    and the epilogue.  Same bits as calculate_vqt_batch_in_db followed by preprocess_batch, exact peak sets against the
+    oracle epilogue, and only the requested results cross PCIe."""
+    audio = synth.polyphonic_chords(12.0, 22050.0, seed=4)
+    db = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    T = db.shape[0]
+    two = pv.AnalysisState(pv.VqtRange())
+    want = two.preprocess_batch(db, FRAME_NS)
+    one = pv.AnalysisState(pv.VqtRange())
+    got = one.calculate_and_preprocess(vqt, audio, HOP, FRAME_NS, vectors=True, return_db=True)
+    np.testing.assert_array_equal(got["db"][0], db)
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    ref = _oracle_run(db, FRAME_NS)
+    _compare(got, 0, ref, T)
+    # peaks only: a small fraction of the 4 * 588 bytes per frame the spectra would cost
+    lean = pv.AnalysisState(pv.VqtRange())
+    res = lean.calculate_and_preprocess(vqt, audio, HOP, FRAME_NS, max_peaks=32, vectors=False)
+    np.testing.assert_array_equal(res["peak_count"], want["peak_count"])
+    np.testing.assert_array_equal(res["peak_indices"], want["peak_indices"][:, :, :32])
+    assert res["d2h_bytes"] == T * (4 + 32 * 4 + 32 * 8 + 4 + 4) < T * 588 * 4 // 5
+    # a second call continues the recurrence: two halves == one call
+    h = T // 2
+    split = pv.AnalysisState(pv.VqtRange())
+    n_half = (h - 1) * HOP + vqt.n_fft
+    a1 = split.calculate_and_preprocess(vqt, audio[:n_half], HOP, FRAME_NS, frames_per_stream=h, vectors=True)
+    a2 = split.calculate_and_preprocess(vqt, audio[h * HOP:], HOP, FRAME_NS, frames_per_stream=T - h, vectors=True)
+    for k in want:
+        np.testing.assert_array_equal(np.concatenate([a1[k], a2[k]], axis=1), want[k], err_msg=k)
+    for s in (two, one, lean, split):
+        s.close()
+
+
+def test_single_call_pipeline_streams(vqt):
+    chords = np.stack([synth.polyphonic_chords(3.0, 22050.0, seed=s) for s in (11, 12, 13, 14, 15)])
+    db = vqt.calculate_vqt_streams_in_db(chords, HOP)
+    S, T, _ = db.shape
+    two = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    want = two.preprocess_batch(db, FRAME_NS, vectors=("x_vqt_smoothed",))
+    one = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    got = one.calculate_and_preprocess(vqt, chords, HOP, FRAME_NS, vectors=("x_vqt_smoothed",))
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+    with pytest.raises(ValueError):
+        one.calculate_and_preprocess(vqt, chords[:3], HOP, FRAME_NS)        # another number of streams
+    with pytest.raises(ValueError):
+        one.calculate_and_preprocess(vqt, chords[:, :vqt.n_fft - 1], HOP, FRAME_NS, frames_per_stream=1)
+    two.close()
+    one.close()
+
+
+def test_all_117_close_tone_cases_through_the_gpu(vqt):
+    # the reference's test_vqt_close_frequencies (lib.rs:16-48), every case: GPU VQT (one batched call over independent
+    # frames) + one GPU epilogue with 117 independent states, frame_time 1100 ms
+    op = orc.default_params()
+    cases = list(range(int(2.6 * 30), 7 * 30 - 15))
+    assert len(cases) == 117
+    frames = []
+    for i in cases:
+        f1 = np.float32(55.0) * np.float32(2.0) ** (np.float32(i) / np.float32(30))
+        f2 = np.float32(55.0) * np.float32(2.0) ** np.float32(np.float32(i) / np.float32(30) + np.float32(1 / 12))
+        frames.append(orc.test_create_sines(op, [f1, f2]))
+    db = vqt.calculate_vqt_frames_in_db(np.stack(frames))
+    a = pv.AnalysisState(pv.VqtRange(), n_streams=len(cases))
+    res = a.preprocess_batch(db[:, None, :], 1100 * 1_000_000, vectors=False)
+    assert res["peak_count"][:, 0].tolist() == [2] * len(cases)
+    a.close()

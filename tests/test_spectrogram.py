@@ -85,3 +85,73 @@ def test_gpu_ring_is_bit_identical_to_the_oracle(built_lib):
         pv.spectrogram_vqt(x, rgb, np.zeros((64, 100, 4), np.uint8), 0)
     with pytest.raises(pv.PvqtRuntimeError):
         pv.spectrogram_vqt(x, rgb, a, 64)            # write index outside the ring
+
+
+# ---- SpectrogramMode::Peaks (update.rs:997-1062) --------------------------------------------------------------------
+def _peak_lists(frames, max_peaks, n, seed):
+    rng = np.random.default_rng(seed)
+    pk = np.zeros((frames, max_peaks, 2), np.float32)
+    cnt = rng.integers(0, max_peaks + 1, frames).astype(np.uint32)
+    for t in range(frames):
+        c = np.sort(rng.uniform(0.0, n - 1.0, int(cnt[t]))).astype(np.float32)
+        pk[t, :cnt[t], 0] = c
+        pk[t, :cnt[t], 1] = rng.uniform(0.0, 40.0, int(cnt[t])).astype(np.float32)
+    if frames > 2:
+        cnt[1] = 0                                   # a frame without peaks leaves its (cleared) row alone
+        pk[2, :cnt[2], 1] = 0.0                      # max_size == 0: nothing is drawn (update.rs:1008)
+    if frames > 3 and cnt[3] >= 2:
+        pk[3, 1, 0] = pk[3, 0, 0] + np.float32(0.7)  # overlapping discs: the later peak owns the shared bins
+    return pk, cnt
+
+
+def test_oracle_peaks_mode_known_answers():
+    # a peak exactly on a semitone takes the crate's colour of that pitch class (times 1.2, clamped): bin 0 of the
+    # default range is A (55 Hz): semitone_offset = 84 - 21 = 63 -> 12 * 63 / 84 = 9 -> COLORS[9] = (1.00, 0.96, 0.03)
+    img = np.zeros((4, 588, 4), np.uint8)
+    pk = np.array([[[84.0, 30.0], [200.5, 15.0]]], np.float32)
+    w = orc.spectrogram_peaks(pk, np.array([2], np.uint32), img, 0)
+    assert w == 1 and not img[:3].any()
+    row = img[3]
+    assert row[84].tolist() == [255, 255, int(np.float32(7 / 255) * np.float32(255) * np.float32(1.2)), 255]
+    lit = np.nonzero(row[:, 3])[0].tolist()
+    # bins floor(c - 2) .. ceil(c + 2) - 1 with |bin - c| <= 2: the half-open range drops bin 86 of the integer centre
+    # (update.rs:1031-1034), an asymmetry of the reference that is kept; alpha at distance 2 is exp(-2) * 306 = 41
+    assert lit == [82, 83, 84, 85, 199, 200, 201, 202]
+    assert row[82, 3] == 41 and row[83, 3] == row[85, 3] == 185
+    # the weaker peak: brightness (1 - 0.25) * 1.5 clamps to 1, falloff exp(-0.25 / 2) -> 270 -> clamp 255
+    assert row[200, 3] == 255 and row[199, 3] == int(np.float32(np.exp(np.float32(-2.25 / 2.0))) * np.float32(306.0))
+    # colours are the LCh round trip of the crate: on a semitone exactly the table colour, halfway the L = 60 gray
+    np.testing.assert_array_equal((orc.calculate_color(84, 7.0) * 255).round(), [2, 132, 181])
+    np.testing.assert_array_equal((orc.calculate_color(84, 3.5) * 255).round(), [145, 145, 145])
+
+
+@pytest.mark.gpu
+def test_gpu_peaks_ring_is_bit_identical_to_the_oracle(built_lib):
+    for frames, mp, h, w0, rng_ in ((1, 64, 256, 0, pv.VqtRange()), (90, 64, 256, 200, pv.VqtRange()),
+                                    (300, 32, 64, 5, pv.VqtRange()), (7, 16, 2, 1, pv.VqtRange(55.0, 2, 24)),
+                                    (5, 8, 1, 0, pv.VqtRange(55.0, 2, 24)), (40, 64, 50, 49, pv.VqtRange(55.0, 8, 168))):
+        n = rng_.n_buckets()
+        pk, cnt = _peak_lists(frames, mp, n, frames + mp)
+        ref = np.random.default_rng(3).integers(0, 256, (h, n, 4), dtype=np.uint8)
+        got = ref.copy()
+        w_ref = orc.spectrogram_peaks(pk, cnt, ref, w0, rng_.buckets_per_octave)
+        w_got = pv.spectrogram_peaks(pk, cnt, got, w0, rng_)
+        assert w_got == w_ref
+        np.testing.assert_array_equal(got, ref)
+    # fed from K-analysis: the peaks of a real recording, two batched calls = one
+    from pitchvis_b200 import synth
+    v = pv.Vqt()
+    a = pv.AnalysisState(pv.VqtRange())
+    res = a.calculate_and_preprocess(v, synth.polyphonic_chords(6.0, 22050.0, seed=5), synth.HOP_DEFAULT, 16_689_342)
+    pk, cnt = res["peaks_continuous"][0], res["peak_count"][0]
+    assert cnt.max() > 3
+    ref = np.zeros((128, 588, 4), np.uint8)
+    got, two = ref.copy(), ref.copy()
+    w_ref = orc.spectrogram_peaks(pk, cnt, ref, 0)
+    assert pv.spectrogram_peaks(pk, cnt, got, 0) == w_ref
+    np.testing.assert_array_equal(got, ref)
+    w = pv.spectrogram_peaks(pk[:100], cnt[:100], two, 0)
+    assert pv.spectrogram_peaks(pk[100:], cnt[100:], two, w) == w_ref
+    np.testing.assert_array_equal(two, ref)
+    a.close()
+    v.close()
