@@ -90,6 +90,10 @@ int         pvqt_device_count(int *count);
 typedef void (*pvqt_log_fn)(int level, const char *message, void *user);
 int         pvqt_set_log_callback(pvqt_log_fn fn, void *user, int max_level);
 
+/* SM count, SM clock (kHz), L2 size (bytes) and host NUMA node (-1: unknown) of a device; any pointer may be NULL.  For
+ * roofline reports (bench.py), so that hosts need no CUDA runtime binding. */
+int         pvqt_device_attributes(int device, int32_t *sm_count, int32_t *sm_clock_khz, int32_t *l2_bytes, int32_t *numa_node);
+
 /* ---- parameters ------------------------------------------------------------- */
 /* `impl Default for VqtParameters` (vqt.rs:333-348, constants vqt.rs:180-214) */
 int pvqt_default_params(pvqt_params *out);
@@ -213,7 +217,8 @@ int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_lau
  * kept selectable).  A mode the kernel does not fit falls back to the next lower one.  Returns the mode in
  * effect. */
 int pvqt_set_fused_epilogue(pvqt *v, int mode);
-/* Plan introspection for tests and bench reports; out[0..n) (n <= 9): cluster size of K-spmm-db's cluster form
+/* Plan introspection for tests and bench reports; out[0..n) (n <= 10; the 10th: bit mask of the window groups that took
+ * the K-sdft path in the most recent batched launch): cluster size of K-spmm-db's cluster form
  * (0: not available), co-resident clusters, shared-memory bytes of its coefficients, rows of its largest
  * part, warps of the one-CTA-per-tile form (0: not available), K-fft block size, columns per spectrum tile,
  * K-sdft plans cached, band slots the warps of one K-spmm-db CTA walk per tile (padding included). */
@@ -246,6 +251,12 @@ int  pvqt_multi_calc_batch_db(pvqt_multi *m, const float *audio, size_t n_sample
 /* Independent streams, contiguous blocks of streams per device. */
 int  pvqt_multi_calc_streams_db(pvqt_multi *m, const float *audio, size_t n_streams, size_t stream_stride,
                                 size_t n_samples, size_t hop, size_t frames_per_stream, float *out);
+
+/* Measurement aid: the host <-> device copy rate of the box with every device of `m` copying at once -- h2d_bytes in
+ * and d2h_bytes out per device and repetition, pinned host memory, both directions in flight, no kernel.  It is the
+ * ceiling of the host-buffer entries above (their end-to-end rate is PCIe-bound).  *seconds: wall time of `reps`
+ * repetitions on all devices. */
+int  pvqt_multi_pcie_probe(pvqt_multi *m, size_t h2d_bytes, size_t d2h_bytes, int reps, double *seconds);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,9 @@ SIGNATURES = {
     "pvqt_abi_version": (C.c_int, []),
     "pvqt_last_error_string": (C.c_char_p, []),
     "pvqt_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pvqt_device_attributes": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32)]),
+    "pvqt_multi_pcie_probe": (C.c_int, [_VP, _SZ, _SZ, C.c_int, C.POINTER(C.c_double)]),
     "pvqt_default_params": (C.c_int, [C.POINTER(PvqtParams)]),
     "pvqt_params_n_buckets": (_SZ, [C.POINTER(PvqtParams)]),
     "pvqt_filter_bank_params": (C.c_int, [C.POINTER(PvqtParams), _VP, _SZ, C.POINTER(PvqtError)]),

@@ -6,6 +6,7 @@
 // kernels of vqt_kernels.cu or fails with PVQT_CUDA_ERROR.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -167,6 +168,11 @@ struct pvqt {
         std::vector<SdftTcPlan> tc;        // per group: plan of the tcgen05 form (n_groups = 0: not available)
     };
     std::vector<SdftPlan> sdft_plans;
+    // Which groups take the K-sdft path is decided from the frames per stream of the WHOLE job, never from the piece a
+    // launch sees: the pipelined host entries cut a job into segments and pvqt_multi_* into shards, and a frame must
+    // get the same bits whatever piece it lands in.  0: no enclosing job, use the launch's own count.
+    size_t sdft_job_frames = 0;
+    uint32_t last_sdft_mask = 0;           // window groups on the K-sdft path in the most recent launch (plan_info)
     bool sdft_enabled = true;              // pvqt_set_sliding_dft
     bool sdft_tensor_cores = true;         // mode 2 of pvqt_set_sliding_dft: partial sums on mma.sync (3xTF32)
     int sdft_tc = 0;                       // 1 (mode 3): tcgen05 partial sums for the groups mode 2 selects; 2 (PVQT_SDFT_TC=2,
@@ -1021,18 +1027,21 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
     // window groups on the sliding partial-DFT path for this call
     const pvqt::SdftPlan *plan = nullptr;
     std::vector<int> sdft_groups;  // indices into plan->groups
-    if (v->sdft_enabled && frames_per_stream > 1) {
+    const size_t job_frames = std::max(frames_per_stream, v->sdft_job_frames);
+    if (v->sdft_enabled && job_frames > 1) {
         int st = PVQT_OK;
         plan = sdft_plan_for(v, hop, &st);
         if (st != PVQT_OK) return st;
         if (plan)
             for (size_t i = 0; i < plan->groups.size(); ++i)
                 if ((int)sdft_groups.size() < kMaxSdft &&
-                    (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, frames_per_stream) ||
-                     (v->sdft_tc >= 2 && frames_per_stream >= 256 && plan->tc[i].n_groups > 0 &&
+                    (sdft_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop, job_frames) ||
+                     (v->sdft_tc >= 2 && job_frames >= 256 && plan->tc[i].n_groups > 0 &&
                       sdft_tc_worthwhile((size_t)plan->groups[i].n_window, (size_t)plan->groups[i].nk, hop))))
                     sdft_groups.push_back((int)i);
     }
+    v->last_sdft_mask = 0;
+    for (int i : sdft_groups) v->last_sdft_mask |= 1u << plan->group_index[(size_t)i];
     auto on_sdft = [&](int gi) {
         for (int i : sdft_groups)
             if (plan->group_index[(size_t)i] == gi) return true;
@@ -1432,6 +1441,11 @@ int run_host(pvqt *v, const float *audio, size_t n_streams, size_t stream_stride
         return fail(PVQT_INVALID_ARGUMENT, "stream_stride must be >= n_samples");
     PVQT_CUDA(cudaSetDevice(v->device));
     J.span = (frames_per_stream - 1) * hop + J.n_fft;  // samples one stream needs
+    struct JobFrames {   // every segment of this call decides its K-sdft groups from the whole call (or the enclosing job)
+        pvqt *v; size_t saved;
+        JobFrames(pvqt *v_, size_t f) : v(v_), saved(v_->sdft_job_frames) { v->sdft_job_frames = std::max(saved, f); }
+        ~JobFrames() { v->sdft_job_frames = saved; }
+    } job_frames(v, frames_per_stream);
 
     const size_t budget = v->staging_budget_samples;
     const bool by_stream = J.span <= budget && (n_streams > 1 || frames_per_stream <= 256);
@@ -1627,6 +1641,21 @@ int pvqt_device_count(int *count)
     if (!count) return fail(PVQT_INVALID_ARGUMENT, "count is null");
     *count = 0;
     PVQT_CUDA(cudaGetDeviceCount(count));
+    return PVQT_OK;
+}
+
+int pvqt_device_attributes(int device, int32_t *sm_count, int32_t *sm_clock_khz, int32_t *l2_bytes, int32_t *numa_node)
+{
+    PVQT_CUDA(cudaSetDevice(device));
+    int v = 0;
+    if (sm_count) { PVQT_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); *sm_count = v; }
+    if (sm_clock_khz) { PVQT_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); *sm_clock_khz = v; }
+    if (l2_bytes) { PVQT_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, device)); *l2_bytes = v; }
+    if (numa_node) {
+        v = -1;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrHostNumaId, device) != cudaSuccess) { cudaGetLastError(); v = -1; }
+        *numa_node = v;
+    }
     return PVQT_OK;
 }
 
@@ -2111,10 +2140,10 @@ int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)
     int32_t walk = 0;   // band slots the warps of one K-spmm-db CTA walk per tile (padding included)
     if (v->fused_capable)
         for (int w = 0; w < v->fused.n_warps; ++w) walk += v->fused.warp[w].width + v->fused.warp[w].nwidth;
-    const int32_t info[9] = {v->cluster_capable ? v->cluster.cluster_size : 0, v->cluster_max_active, v->cluster.coef_bytes,
-                             v->cluster.max_rows, v->fused_capable ? v->fused.n_warps : 0, v->fft_block_threads,
-                             v->fft.spec_stride, (int32_t)v->sdft_plans.size(), walk};
-    for (size_t i = 0; i < n && i < 9; ++i) out[i] = info[i];
+    const int32_t info[10] = {v->cluster_capable ? v->cluster.cluster_size : 0, v->cluster_max_active, v->cluster.coef_bytes,
+                              v->cluster.max_rows, v->fused_capable ? v->fused.n_warps : 0, v->fft_block_threads,
+                              v->fft.spec_stride, (int32_t)v->sdft_plans.size(), walk, (int32_t)v->last_sdft_mask};
+    for (size_t i = 0; i < n && i < 10; ++i) out[i] = info[i];
     return PVQT_OK;
 }
 
@@ -2256,8 +2285,60 @@ int pvqt_multi_calc_batch_db(pvqt_multi *m, const float *audio, size_t n_samples
         pvqt_shard_range(n_frames, m->handles.size(), i, &f0, &f1);
         if (f1 == f0) return (int)PVQT_OK;
         pvqt_frame_range_samples(n_fft, hop, f0, f1, &s0, &s1);
-        return pvqt_calc_batch_db(m->handles[i], audio + s0, s1 - s0, hop, f1 - f0, out + f0 * nb);
+        pvqt *h = m->handles[i];
+        h->sdft_job_frames = n_frames;   // the shard takes the code path of the whole recording: same bits as unsharded
+        const int rc = pvqt_calc_batch_db(h, audio + s0, s1 - s0, hop, f1 - f0, out + f0 * nb);
+        h->sdft_job_frames = 0;
+        return rc;
     });
+}
+
+// What the host <-> device links of the box carry when every device of `m` copies at once: h2d_bytes in and d2h_bytes out
+// per device and repetition, from / to pinned host memory, the two directions on their own streams -- the same traffic
+// the host-buffer entries generate, without any kernel.  *seconds = wall time of `reps` repetitions on all devices.
+int pvqt_multi_pcie_probe(pvqt_multi *m, size_t h2d_bytes, size_t d2h_bytes, int reps, double *seconds)
+{
+    if (!m || m->handles.empty() || !seconds || reps <= 0) return fail(PVQT_INVALID_ARGUMENT, "bad probe request");
+    const size_t n = m->handles.size();
+    std::vector<void *> h_in(n, nullptr), h_out(n, nullptr), d_in(n, nullptr), d_out(n, nullptr);
+    int rc = for_each_device(m, [&](size_t i) {
+        pvqt *v = m->handles[i];
+        PVQT_CUDA(cudaSetDevice(v->device));
+        PVQT_CUDA(cudaHostAlloc(&h_in[i], std::max<size_t>(h2d_bytes, 16), cudaHostAllocPortable));
+        PVQT_CUDA(cudaHostAlloc(&h_out[i], std::max<size_t>(d2h_bytes, 16), cudaHostAllocPortable));
+        PVQT_CUDA(cudaMalloc(&d_in[i], std::max<size_t>(h2d_bytes, 16)));
+        PVQT_CUDA(cudaMalloc(&d_out[i], std::max<size_t>(d2h_bytes, 16)));
+        std::memset(h_in[i], 0, std::max<size_t>(h2d_bytes, 16));
+        PVQT_CUDA(cudaMemset(d_out[i], 0, std::max<size_t>(d2h_bytes, 16)));
+        PVQT_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], h2d_bytes, cudaMemcpyHostToDevice, v->s_in));   // warm-up
+        PVQT_CUDA(cudaMemcpyAsync(h_out[i], d_out[i], d2h_bytes, cudaMemcpyDeviceToHost, v->s_out));
+        PVQT_CUDA(cudaStreamSynchronize(v->s_in));
+        PVQT_CUDA(cudaStreamSynchronize(v->s_out));
+        return (int)PVQT_OK;
+    });
+    if (rc == PVQT_OK) {
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = for_each_device(m, [&](size_t i) {
+            pvqt *v = m->handles[i];
+            PVQT_CUDA(cudaSetDevice(v->device));
+            for (int r = 0; r < reps; ++r) {
+                if (h2d_bytes) PVQT_CUDA(cudaMemcpyAsync(d_in[i], h_in[i], h2d_bytes, cudaMemcpyHostToDevice, v->s_in));
+                if (d2h_bytes) PVQT_CUDA(cudaMemcpyAsync(h_out[i], d_out[i], d2h_bytes, cudaMemcpyDeviceToHost, v->s_out));
+            }
+            PVQT_CUDA(cudaStreamSynchronize(v->s_in));
+            PVQT_CUDA(cudaStreamSynchronize(v->s_out));
+            return (int)PVQT_OK;
+        });
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    for (size_t i = 0; i < n; ++i) {
+        cudaSetDevice(m->handles[i]->device);
+        if (h_in[i]) cudaFreeHost(h_in[i]);
+        if (h_out[i]) cudaFreeHost(h_out[i]);
+        if (d_in[i]) cudaFree(d_in[i]);
+        if (d_out[i]) cudaFree(d_out[i]);
+    }
+    return rc;
 }
 
 int pvqt_multi_calc_streams_db(pvqt_multi *m, const float *audio, size_t n_streams, size_t stream_stride,

@@ -255,10 +255,10 @@ class Vqt:
         return int(self._lib.pvqt_set_fused_epilogue(self._h, int(mode)))
 
     def plan_info(self) -> dict:
-        out = (C.c_int32 * 9)()
-        _check(self._lib.pvqt_plan_info(self._h, out, 9))
+        out = (C.c_int32 * 10)()
+        _check(self._lib.pvqt_plan_info(self._h, out, 10))
         keys = ("cluster_size", "clusters_resident", "cluster_coef_bytes", "cluster_max_rows", "fused_warps",
-                "fft_block_threads", "spec_stride", "sdft_plans", "fused_walk_slots")
+                "fft_block_threads", "spec_stride", "sdft_plans", "fused_walk_slots", "sdft_group_mask")
         return dict(zip(keys, [int(x) for x in out]))
 
     def set_sliding_dft(self, mode) -> int:
@@ -406,6 +406,19 @@ class MultiVqt:
             self.close()
         except Exception:
             pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def device_handle(self, index: int) -> C.c_void_p:
+        return C.c_void_p(self._lib.pvqt_multi_handle(self._h, index))
+
+    def pcie_probe(self, h2d_bytes: int, d2h_bytes: int, reps: int = 5) -> float:
+        """Seconds for `reps` x (h2d_bytes in + d2h_bytes out) on every device at once (pvqt_multi_pcie_probe)."""
+        s = C.c_double()
+        _check(self._lib.pvqt_multi_pcie_probe(self._h, h2d_bytes, d2h_bytes, reps, C.byref(s)))
+        return float(s.value)
 
     def calculate_vqt_batch_in_db(self, audio, hop: int, n_frames: Optional[int] = None) -> np.ndarray:
         audio = _as_f32(audio, "audio")

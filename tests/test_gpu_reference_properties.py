@@ -92,7 +92,7 @@ def test_results_do_not_depend_on_addresses_hops_or_shards():
     m2 = pv.MultiVqt(p, devs[:2])
     try:
         n_frames = 41
-        audio = synth.polyphonic_chords(2.0, 44100.0, seed=21)[:p.n_fft + (n_frames - 1) * hop]
+        audio = synth.polyphonic_chords(3.0, 44100.0, seed=21)[:p.n_fft + (n_frames - 1) * hop]
         frames = np.stack([audio[t * hop:t * hop + p.n_fft] for t in range(n_frames)])
         for sliding in (False, True):
             v.set_sliding_dft(sliding)
