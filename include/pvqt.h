@@ -212,10 +212,11 @@ uint64_t pvqt_launch_count(const pvqt *v);
 int pvqt_set_profiling(pvqt *v, int enabled);
 int pvqt_get_profile(pvqt *v, int reset, double *kernel_ms, uint64_t *kernel_launches);
 /* Test / tuning switch for the SpMM + power_to_db stage: 0 = unfused K-spmm + K-db pair, 1 = K-spmm-db with
- * one CTA per tile (default), 2 = K-spmm-db in its cluster form (coefficients stationary in shared memory,
- * frame max / min exchanged through distributed shared memory; measured slower at the default parameters,
- * kept selectable).  A mode the kernel does not fit falls back to the next lower one.  Returns the mode in
- * effect. */
+ * one CTA per tile, 2 = K-spmm-db in its cluster form (coefficients stationary in shared memory, frame max / min
+ * exchanged through distributed shared memory; measured slower at the default parameters, kept selectable),
+ * 3 (default where the kernel fits) = K-spmm-db as a persistent warp-specialised pipeline: one CTA per SM, helper
+ * warps stage / combine the next tile and convert the previous one while the band walk runs.  0, 1 and 3 give the
+ * same bits.  A mode the kernel does not fit falls back (3 -> 1 -> 0).  Returns the mode in effect. */
 int pvqt_set_fused_epilogue(pvqt *v, int mode);
 /* Plan introspection for tests and bench reports; out[0..n) (n <= 10; the 10th: bit mask of the window groups that took
  * the K-sdft path in the most recent batched launch): cluster size of K-spmm-db's cluster form

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -147,10 +148,14 @@ struct pvqt {
     FusedParams fused{};                // K-spmm-db plan (one CTA per tile owns every row)
     bool fused_capable = false;         // false: the kernel is too large for one CTA -> K-spmm + K-db
     bool fused_ok = false;              // fused_capable and not switched off (pvqt_set_fused_epilogue)
+    bool pipe_capable = false, pipe_ok = false;   // K-spmm-db as a persistent warp-specialised pipeline (spmm_pipe.cu)
+    int pipe_sdft_configured = -1;                // combine staging (float2 per K-sdft group) the kernel's smem limit covers
+    int sm_count = 148;
     ClusterParams cluster{};            // K-spmm-db, cluster form (coefficients stationary in shared memory)
     bool cluster_capable = false, cluster_ok = false;
     int cluster_max_active = 0;         // co-resident clusters (cudaOccupancyMaxActiveClusters)
     int fft_block_threads = 256;
+    int fft_wave_ctas = 0;              // > 0: K-fft as at most this many persistent CTAs (PVQT_FFT_WAVE); 0: one item per CTA
     float ref_db = 0.0f;
     std::vector<uint32_t> col_lo, n_cols, spec_off;
     size_t first_sample_used = 0;
@@ -517,6 +522,71 @@ int build_fused_plan(pvqt *v)
         units.insert(units.end(), pos.begin() + (long)best_at, pos.end());
     }
     const int n_warps = (int)((units.size() + 31) / 32);
+    // Which warp walks which group of 32 units.  Warp w issues on SM sub-partition w % 4, and the walk is bound by the
+    // FMA pipe of the busiest sub-partition: the groups (longest walk first) go to the sub-partition with the least
+    // work so far that still has a free warp (groups sorted by length would put the three longest-but-one on
+    // sub-partition 0: 128 / 115 / 86 / 80 slots at the defaults instead of ~102 each).
+    {
+        std::vector<int> walk((size_t)n_warps, 0);
+        for (int w = 0; w < n_warps; ++w) {
+            int a = 0, b = 0;
+            for (size_t i = (size_t)w * 32; i < std::min(units.size(), (size_t)(w + 1) * 32); ++i) {
+                a = std::max(a, units[i].len);
+                b = std::max(b, units[i].nlen);
+            }
+            walk[(size_t)w] = a + b;
+        }
+        std::vector<int> order((size_t)n_warps);
+        for (int w = 0; w < n_warps; ++w) order[(size_t)w] = w;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return walk[(size_t)x] > walk[(size_t)y]; });
+        int cap[4];
+        for (int s = 0; s < 4; ++s) cap[s] = (n_warps - s + 3) / 4;     // warps s, s + 4, s + 8, ...
+        std::vector<int> group_of_warp((size_t)n_warps, -1), bin_of((size_t)n_warps, 0), best_bin;
+        // exhaustive for the usual handful of warps (10 at the defaults: 25,200 assignments), greedy beyond
+        long best_max = -1, nodes = 0;
+        {
+            int load[4] = {0, 0, 0, 0}, used[4] = {0, 0, 0, 0};
+            std::function<void(int)> place = [&](int at) {
+                if (++nodes > 4000000) return;
+                const long cur = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+                if (best_max >= 0 && cur >= best_max) return;
+                if (at == n_warps) { best_max = cur; best_bin = bin_of; return; }
+                const int g = order[(size_t)at];
+                for (int s = 0; s < 4; ++s) {
+                    if (used[s] >= cap[s]) continue;
+                    bool twin = false;                                  // an equally filled, equally sized bin was tried already
+                    for (int s2 = 0; s2 < s; ++s2) twin |= load[s2] == load[s] && used[s2] == used[s] && cap[s2] == cap[s];
+                    if (twin) continue;
+                    load[s] += walk[(size_t)g]; ++used[s]; bin_of[(size_t)g] = s;
+                    place(at + 1);
+                    load[s] -= walk[(size_t)g]; --used[s];
+                }
+            };
+            place(0);
+        }
+        {
+            int used[4] = {0, 0, 0, 0}, load[4] = {0, 0, 0, 0};
+            for (int g : order) {
+                int bin = -1;
+                if (best_max >= 0) {
+                    bin = best_bin[(size_t)g];
+                } else {
+                    for (int s = 0; s < 4; ++s)
+                        if (used[s] < cap[s] && (bin < 0 || load[s] < load[bin])) bin = s;
+                }
+                group_of_warp[(size_t)(bin + 4 * used[bin])] = g;
+                load[bin] += walk[(size_t)g];
+                ++used[bin];
+            }
+        }
+        std::vector<Unit> permuted;
+        permuted.reserve((size_t)n_warps * 32);
+        for (int w = 0; w < n_warps; ++w) {
+            const size_t g = (size_t)group_of_warp[(size_t)w];
+            for (size_t i = g * 32; i < (g + 1) * 32; ++i) permuted.push_back(i < units.size() ? units[i] : Unit{});
+        }
+        units.swap(permuted);   // trailing empty units of a short group walk nothing and own no rows
+    }
     n_cols = std::min<int>((n_cols + 7) & ~7, F.spec_stride);
     // columns the unpredicated band walk may read: start column + the warp's (padded) width; bounded by
     // n_cols + the longest band + the 7-column placement shift
@@ -601,11 +671,20 @@ int build_fused_plan(pvqt *v)
             }
         }
     }
+    if (std::getenv("PVQT_DEBUG_PLAN")) {
+        int sub[4] = {0, 0, 0, 0};
+        for (int w = 0; w < n_warps; ++w) {
+            std::fprintf(stderr, "K-spmm-db warp %d: %d band + %d conjugate-part slots\n", w, warps[(size_t)w].width, warps[(size_t)w].nwidth);
+            sub[w & 3] += warps[(size_t)w].width + warps[(size_t)w].nwidth;
+        }
+        std::fprintf(stderr, "slots per SM sub-partition: %d %d %d %d\n", sub[0], sub[1], sub[2], sub[3]);
+    }
     values.resize(values.size() + (size_t)2 * kFusedRing * H * 32, make_float4(0.f, 0.f, 0.f, 0.f));  // prefetch overrun
     // Every CTA walks the same coefficients in the same order; identical copies at different addresses (CTA b
     // streams copy b % copies) would spread the requests over more L2 slices.  Measured with 16 copies on B200:
     // no change (DESIGN.md, K-spmm-db), so one copy is kept; the mechanism stays for larger kernels.
-    const uint32_t copies = 1;
+    uint32_t copies = 1;
+    if (const char *e = std::getenv("PVQT_VALUE_COPIES")) copies = (uint32_t)std::max(1, std::min(std::atoi(e), 64));
     const size_t one = values.size();
     values.resize(one * copies);
     for (uint32_t c = 1; c < copies; ++c) std::copy(values.begin(), values.begin() + (long)one, values.begin() + (long)(one * c));
@@ -633,6 +712,19 @@ int build_fused_plan(pvqt *v)
     P.ref_db = v->ref_db;
     if ((e = configure_fused(n_warps, P.cols_touched, P.n_buckets, R)) != cudaSuccess)
         return cuda_fail(e, "configure spmm_db_fused_kernel");
+    // the persistent pipeline form (default where it fits: two plane sets + two log-spectrum buffers in one CTA)
+    int min_slots = 1 << 30;
+    for (int w = 0; w < n_warps; ++w) min_slots = std::min(min_slots, warps[(size_t)w].width + warps[(size_t)w].nwidth);
+    v->pipe_capable = pipe_supported(n_warps, P.cols_touched, P.n_buckets, R, min_slots);
+    if (v->pipe_capable && configure_pipe(n_warps, P.cols_touched, P.n_buckets, 0) != cudaSuccess) {
+        cudaGetLastError();
+        v->pipe_capable = false;
+    }
+    v->pipe_sdft_configured = 0;
+    P.plane_stride = pipe_plane_stride(P.cols_touched);
+    v->pipe_ok = v->pipe_capable;
+    if (const char *m = std::getenv("PVQT_SPMM_PIPE")) v->pipe_ok = v->pipe_capable && std::atoi(m) != 0;
+    if (cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, v->device) != cudaSuccess) v->sm_count = 148;
     return PVQT_OK;
 }
 
@@ -958,8 +1050,9 @@ int build_cluster_plan(pvqt *v)
     v->cluster_capable = true;
     v->cluster_ok = false;  // measured slower than the one-CTA-per-tile form on B200: opt-in, mode 2
     if (const char *m = std::getenv("PVQT_SPMM_MODE")) {
-        v->cluster_ok = std::atoi(m) >= 2;
+        v->cluster_ok = std::atoi(m) == 2;
         v->fused_ok = v->fused_capable && std::atoi(m) >= 1;
+        v->pipe_ok = v->pipe_ok && v->fused_ok && std::atoi(m) != 1;
     }
     return PVQT_OK;
 }
@@ -984,7 +1077,9 @@ void prof_end(pvqt *v, cudaStream_t stream)
 int reserve_scratch(pvqt *v, pvqt::Lane &L, size_t frames, bool need_power, cudaStream_t stream)
 {
     frames = std::min<size_t>(frames, v->chunk_frames);
-    const size_t tile_bytes = (size_t)v->fft.spec_stride * kTileFrames * 2 * sizeof(float);
+    // a tile in the record layout, or in the plane layout of the pipeline form of K-spmm-db (whichever is larger)
+    const size_t tile_bytes = std::max((size_t)v->fft.spec_stride * kTileFrames * 2 * sizeof(float),
+                                       v->pipe_capable ? (size_t)v->fused.plane_stride * kTileFrames * 2 * sizeof(float) : 0);
     const size_t want = ((frames + kTileFrames - 1) / kTileFrames) * tile_bytes;
     if (want > L.spec.bytes) {
         cudaError_t e = L.spec.reserve(want);
@@ -1119,6 +1214,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             if (!sd.empty()) {
                 size_t need = 0;
                 for (const auto &sp : sd) need += (size_t)sp.n_streams * sp.rows_per_stream * sp.g.nk * sizeof(float2);
+                need += 64;   // the pipeline form's bulk copies round their ends to 16 bytes
                 if (L.sdft_c.reserve(need) != cudaSuccess || L.sdft_r.reserve(need) != cudaSuccess)
                     return cuda_fail(cudaGetLastError(), "allocate K-sdft scratch");
                 size_t off = 0;
@@ -1147,28 +1243,60 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 }
             }
 
+            // ---- K-spmm-db form of this launch: the pipeline form needs the combine staging of this hop's K-sdft groups
+            // to fit beside its planes (else the one-CTA-per-tile form), and K-fft then writes the plane layout
+            int pipe_sdft = 0;
+            bool use_pipe = v->pipe_ok && v->fused_ok && !v->cluster_ok && !d_spec_out && !(v->tile_flags && !v->use_graphs && !v->capturing);
+            if (use_pipe) {
+                for (const auto &sp : sd) pipe_sdft = std::max<int>(pipe_sdft, (int)pipe_sdft_floats2(sp.g.q, sp.g.nk));
+                if (pipe_smem_bytes(v->fused.cols_touched, v->fused.n_buckets, v->fused.n_warps, pipe_sdft) > 227 * 1024) {
+                    use_pipe = false;
+                } else if (pipe_sdft > v->pipe_sdft_configured) {
+                    if (configure_pipe(v->fused.n_warps, v->fused.cols_touched, v->fused.n_buckets, pipe_sdft) != cudaSuccess) {
+                        cudaGetLastError();
+                        use_pipe = false;
+                    } else {
+                        v->pipe_sdft_configured = pipe_sdft;
+                    }
+                }
+            }
+
             // ---- K-fft for the other groups ----
             FftParams fp = v->fft;
+            fp.plane_stride = use_pipe ? v->fused.plane_stride : 0;
             fp.frames.audio = d_audio;
             fp.frames.stream_stride = stream_stride;
             fp.frames.hop = hop;
             fp.frames.frames_per_stream = (uint32_t)frames_per_stream;
             fp.frames.n_frames = n;
             fp.frames.first_frame = f0;
+            fp.frames.first_stream = (uint32_t)s0;
+            fp.frames.first_t = (uint32_t)t0;
             fp.spec = spec;
             fp.wait_prior = sd.empty() ? 0 : 1;
             int ctas = 0, kept = 0;
+            // One wave: the launch's work items (frames_per_cta frames each, about the same work whatever the group) are
+            // spread over at most fft_wave CTAs, each group a share proportional to its items, and every CTA loops over
+            // its items -- no last, mostly empty wave (5.19 waves of one-item CTAs at 3507 frames before).
+            size_t items_total = 0;
+            for (int g = 0; g < v->fft.n_groups; ++g)
+                if (!on_sdft(g)) items_total += (n + v->fft.group[g].frames_per_cta - 1) / v->fft.group[g].frames_per_cta;
+            const size_t wave = (size_t)v->fft_wave_ctas;
             for (int g = 0; g < v->fft.n_groups; ++g) {
                 if (on_sdft(g)) continue;
                 fp.group[kept] = v->fft.group[g];
                 fp.group[kept].cta_begin = ctas;
-                ctas += (int)((n + fp.group[kept].frames_per_cta - 1) / fp.group[kept].frames_per_cta);
+                const size_t items = (n + fp.group[kept].frames_per_cta - 1) / fp.group[kept].frames_per_cta;
+                size_t share = (wave == 0 || items_total <= wave) ? items : std::max<size_t>(1, (items * wave + items_total / 2) / items_total);
+                share = std::min(share, items);
+                fp.group[kept].n_ctas = (int32_t)share;
+                ctas += (int)share;
                 ++kept;
             }
             fp.n_groups = kept;
             fp.n_sdft = 0;
             // per-tile completion counts for K-spmm-db (one-CTA form only; not under graph capture; K-sdft must report too)
-            const bool flags = v->tile_flags && !v->use_graphs && !v->capturing && v->fused_ok && !v->cluster_ok && !d_spec_out &&
+            const bool flags = !use_pipe && v->tile_flags && !v->use_graphs && !v->capturing && v->fused_ok && !v->cluster_ok && !d_spec_out &&
                                kept > 0 && counted;
             fp.tile_ready = nullptr;
             if (flags) {
@@ -1236,7 +1364,7 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
                 up.n_ready_groups = fp.n_groups;
                 for (int g = 0; g < fp.n_groups; ++g) up.ready_fpc[g] = fp.group[g].frames_per_cta;
                 prof_begin(v, 3, stream);
-                e = launch_spmm_db_fused(up, stream);
+                e = use_pipe ? launch_spmm_db_pipe(up, v->sm_count, pipe_sdft, stream) : launch_spmm_db_fused(up, stream);
                 if (e != cudaSuccess) return cuda_fail(e, "launch spmm_db_fused_kernel");
                 prof_end(v, stream);
                 v->launches.fetch_add(1);
@@ -1584,7 +1712,7 @@ int run_instant(pvqt *v, const float *x, float *out)
         PVQT_CUDA(cudaMemcpyAsync(I.h_out, I.d_out, nb * sizeof(float), cudaMemcpyDeviceToHost, v->stream));
         return PVQT_OK;
     };
-    const int config = (v->fused_ok ? 1 : 0) | (v->cluster_ok ? 2 : 0);
+    const int config = (v->fused_ok ? 1 : 0) | (v->cluster_ok ? 2 : 0) | (v->pipe_ok ? 4 : 0);
     if (I.exec && (I.scratch_generation != v->lane[0].spec.generation || I.config != config)) {
         cudaGraphExecDestroy(I.exec);
         I.exec = nullptr;
@@ -1832,8 +1960,16 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
     if (const char *s = std::getenv("PVQT_CHUNK_FRAMES"))   // frames per launch (tuning); kept a multiple of two tiles
         v->chunk_frames = (uint32_t)std::max(2 * kTileFrames, std::min(std::atoi(s), 1 << 20) / (2 * kTileFrames) * (2 * kTileFrames));
     if (const char *s = std::getenv("PVQT_SDFT_TC")) v->sdft_tc = std::max(0, std::min(std::atoi(s), 2));
+    if (cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) v->sm_count = 148;
     pvqt *raw = v.release();
     int rc = build_device_plan(raw);
+    if (rc == PVQT_OK) {
+        // 0 (default): one work item per CTA, the hardware's CTA scheduler balances the SMs.  Measured against one wave of
+        // persistent CTAs looping over their items (PVQT_FFT_WAVE=592: 4 resident CTAs x 148 SMs): 45.5 us against 51.8 us
+        // per 3507 frames -- the static split loses more to imbalance than the last, partly empty wave costs.
+        raw->fft_wave_ctas = 0;
+        if (const char *s = std::getenv("PVQT_FFT_WAVE")) raw->fft_wave_ctas = std::max(0, std::atoi(s));
+    }
     if (rc != PVQT_OK) {
         err->status = rc;
         std::string keep = g_last_error;
@@ -2128,10 +2264,11 @@ int pvqt_set_profiling(pvqt *v, int enabled)
 int pvqt_set_fused_epilogue(pvqt *v, int mode)
 {
     if (!v) return 0;
-    v->cluster_ok = v->cluster_capable && mode >= 2;
+    v->cluster_ok = v->cluster_capable && mode == 2;
     v->fused_ok = v->fused_capable && mode >= 1;
+    v->pipe_ok = v->pipe_capable && v->fused_ok && mode >= 3;
     if (v->graph_exec) { cudaGraphExecDestroy(v->graph_exec); v->graph_exec = nullptr; }
-    return v->cluster_ok ? 2 : (v->fused_ok ? 1 : 0);
+    return v->cluster_ok ? 2 : (v->pipe_ok ? 3 : (v->fused_ok ? 1 : 0));
 }
 
 int pvqt_plan_info(const pvqt *v, int32_t *out, size_t n)

@@ -35,6 +35,16 @@ __host__ __device__ inline size_t spec_index_im(size_t frame, int col, int spec_
     return (tile * spec_stride + col) * (2 * kTileFrames) + (chunk << 2) + (fi & 3);
 }
 
+// Spectrum scratch layout "planes" (the pipeline form of K-spmm-db, spmm_pipe.cu): [tile][chunk 0..3][column < plane_stride]
+// [4 floats] -- chunk 0,1 = Re of frames 0-3, 4-7; 2,3 = Im -- exactly the shared-memory image K-spmm-db walks, so a
+// tile is staged with ONE bulk copy (cp.async.bulk) instead of 3300 16-byte cp.asyncs.  Columns nobody writes stay zero.
+__host__ __device__ inline size_t plane_index(size_t frame, int col, int plane_stride, int imag)
+{
+    const size_t tile = frame / kTileFrames;
+    const int fi = (int)(frame % kTileFrames);
+    return ((tile * 4 + (size_t)(2 * imag + (fi >> 2))) * plane_stride + col) * 4 + (fi & 3);
+}
+
 // One window group (WindowGroup, vqt.rs:388-404) as the FFT kernel sees it.
 struct FftGroup {
     int32_t  window_begin;   // first sample of the window inside an n_fft frame
@@ -42,8 +52,8 @@ struct FftGroup {
     int32_t  col_lo, col_hi; // consumed real-FFT bins [col_lo, col_hi]
     int32_t  spec_offset;    // position of col_lo inside a frame's spectrum row
     int32_t  cta_begin;      // first CTA of this group in the fused launch
-    int32_t  frames_per_cta;
-    int32_t  _pad;
+    int32_t  frames_per_cta; // frames one work item (one trip of a CTA) transforms
+    int32_t  n_ctas;         // CTAs of this group; CTA c works on items c, c + n_ctas, c + 2 n_ctas, ...
     const float2 *twiddle[kMaxFftPasses];  // per-pass tables, [ (r-1)*Ns + k ]
     const float2 *split_twiddle;           // exp(-2 pi i c / N), c = col_lo..col_hi
 };
@@ -56,6 +66,8 @@ struct FrameLayout {
     uint32_t frames_per_stream;
     uint32_t n_frames;        // frames in this launch
     uint64_t first_frame;     // global index of local frame 0 (for addressing `audio`)
+    uint32_t first_stream;    // first_frame = first_stream * frames_per_stream + first_t (32-bit arithmetic in the kernels)
+    uint32_t first_t;
 };
 
 // Sliding partial-DFT path of one window group ("K-sdft").  When consecutive frames overlap (hop H much
@@ -115,6 +127,7 @@ struct FftParams {
     int32_t     spec_stride;  // columns per tile (multiple of 8)
     FrameLayout frames;
     float      *spec;         // tiled planar layout, ceil(n_frames / 8) tiles
+    int32_t     plane_stride; // > 0: write the "planes" layout with this many columns per plane (spec_stride unused)
     int32_t     wait_prior;   // 1: launched programmatically behind K-sdft, wait for it before exiting
     int32_t     n_sdft;       // K-sdft groups whose combine step the CTAs of FFT group `combine_group` run
     int32_t     combine_group;
@@ -202,6 +215,7 @@ struct FusedParams {
     float   *out_db;           // [n_frames][n_buckets]
     float   *power;            // optional [n_frames][n_buckets]
     float    ref_db;
+    int32_t  plane_stride;     // pipeline form: columns per plane of the "planes" scratch layout (= the kernel's PLANE)
     int32_t  n_sdft;           // K-sdft groups whose combine step this kernel runs while it stages the tile
     const unsigned *sdft_done; // completion counter of the partial-sum launches (nullptr: combine after the grid wait)
     uint32_t sdft_expected;    // counter value once every partial-sum CTA of this launch has finished (modulo 2^32)
@@ -290,6 +304,13 @@ cudaError_t launch_spmm_db_cluster(const ClusterParams &p, int n_clusters, cudaS
 bool        fused_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane);
 size_t      fused_smem_bytes(int cols_touched, int n_buckets, int n_warps, int rows_per_lane);
 cudaError_t configure_fused(int n_warps, int cols_touched, int n_buckets, int rows_per_lane);
+// K-spmm-db, persistent warp-specialised pipeline form (spmm_pipe.cu): same FusedParams plan, one CTA per SM
+bool        pipe_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane, int min_slots);
+int         pipe_plane_stride(int cols_touched);          // columns per plane of the scratch layout the kernel stages
+size_t      pipe_smem_bytes(int cols_touched, int n_buckets, int n_warps, int sdft_floats2);
+size_t      pipe_sdft_floats2(int q, int nk);             // float2 entries of the combine's staging for one K-sdft group
+cudaError_t configure_pipe(int n_warps, int cols_touched, int n_buckets, int sdft_floats2);
+cudaError_t launch_spmm_db_pipe(const FusedParams &p, int n_ctas, int sdft_floats2, cudaStream_t stream);
 cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);
 size_t spmm_smem_bytes(int max_cols);

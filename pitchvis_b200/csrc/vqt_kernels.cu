@@ -261,18 +261,15 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
                 (void)dummy;
                 const int q = out_index<R>(j);
                 const int off = NS == 1 ? q : q * (NS + NS / 16);
-                if constexpr (kLast) {
-                    const int o = j0 + q * NS;
-                    if (o <= g.col_hi || o >= NC - g.col_hi) p[off] = v[i * R + j];
-                } else {
-                    p[off] = v[i * R + j];
-                }
+                // last pass: every output of a butterfly that is needed at all is stored (two compares and a predicate
+                // per output cost more than the store; butterflies with no consumed output were skipped above)
+                p[off] = v[i * R + j];
             }
         } else {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int o = j0 + out_index<R>(j) * NS;
-                if (!kLast || o <= g.col_hi || o >= NC - g.col_hi) s[pad_index(o)] = v[i * R + j];
+                s[pad_index(o)] = v[i * R + j];
             }
         }
     }
@@ -290,12 +287,20 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
     const int tid = threadIdx.x;
     const int fid = tid / T;
     const int t = tid - fid * T;
-    const uint32_t local_frame = (blockIdx.x - g.cta_begin) * FPC + fid;
+    float2 *s = smem + fid * pad_index(NC);
+    // One wave of CTAs: CTA c of the group transforms the frames of work items c, c + n_ctas, ... (an item = FPC frames),
+    // so that every SM finishes at about the same time instead of a last, mostly empty wave of one-item CTAs.
+    const uint32_t n_items = (P.frames.n_frames + FPC - 1) / FPC;
+#pragma unroll 1
+    for (uint32_t item = blockIdx.x - g.cta_begin; item < n_items; item += (uint32_t)g.n_ctas) {
+    const uint32_t local_frame = item * FPC + fid;
     const bool valid = local_frame < P.frames.n_frames;
 
-    const uint64_t f = P.frames.first_frame + (valid ? local_frame : 0);
-    const uint64_t stream = f / P.frames.frames_per_stream;
-    const uint64_t in_stream = f - stream * P.frames.frames_per_stream;
+    // frame -> (stream, frame in stream), 32-bit: frames_per_stream < 2^31 and n_frames <= 2^20 per launch
+    const uint32_t ft = P.frames.first_t + (valid ? local_frame : 0);
+    const uint32_t ds = ft / P.frames.frames_per_stream;
+    const uint64_t stream = (uint64_t)P.frames.first_stream + ds;
+    const uint64_t in_stream = ft - ds * P.frames.frames_per_stream;
     const float *x = P.frames.audio + stream * P.frames.stream_stride + in_stream * P.frames.hop + g.window_begin;
     // The nested windows are centred, so at the defaults every window starts on an odd sample and the packed loads
     // z[m] = (x[2m], x[2m+1]) would be 4-byte loads.  Transform the window moved one sample down instead (8-byte
@@ -317,7 +322,6 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
         if (valid) edge = __ldg(x + 2 * NC) - __ldg(x);
     }
 
-    float2 *s = smem + fid * pad_index(NC);
     float2 v[kPointsPerThread];
     fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g);
 
@@ -336,9 +340,16 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
             const float2 w = __ldg(g.split_twiddle + i);
             float2 xc = cadd(e, cmul(o, w));
             if (shifted) xc = cmul(make_float2(xc.x + edge, xc.y), make_float2(w.x, -w.y));   // W^-c = conj(w)
-            P.spec[spec_index_re(local_frame, g.spec_offset + i, P.spec_stride)] = xc.x;
-            P.spec[spec_index_im(local_frame, g.spec_offset + i, P.spec_stride)] = xc.y;
+            if (P.plane_stride > 0) {
+                P.spec[plane_index(local_frame, g.spec_offset + i, P.plane_stride, 0)] = xc.x;
+                P.spec[plane_index(local_frame, g.spec_offset + i, P.plane_stride, 1)] = xc.y;
+            } else {
+                P.spec[spec_index_re(local_frame, g.spec_offset + i, P.spec_stride)] = xc.x;
+                P.spec[spec_index_im(local_frame, g.spec_offset + i, P.spec_stride)] = xc.y;
+            }
         }
+    }
+    fft_sync<T, BLOCK>(fid);   // the next item's first pass overwrites the buffer the split step has just read
     }
 }
 
@@ -386,9 +397,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : (B
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t lf0 = (blockIdx.x - g.cta_begin) * g.frames_per_cta;
-            const uint32_t lf1 = min(lf0 + (uint32_t)g.frames_per_cta, P.frames.n_frames);
-            for (uint32_t tl = lf0 / kTileFrames; tl * kTileFrames < lf1; ++tl) atomicAdd(P.tile_ready + tl, 1u);
+            const uint32_t n_items = (P.frames.n_frames + g.frames_per_cta - 1) / g.frames_per_cta;
+            for (uint32_t item = blockIdx.x - g.cta_begin; item < n_items; item += (uint32_t)g.n_ctas) {
+                const uint32_t lf0 = item * g.frames_per_cta;
+                const uint32_t lf1 = min(lf0 + (uint32_t)g.frames_per_cta, P.frames.n_frames);
+                for (uint32_t tl = lf0 / kTileFrames; tl * kTileFrames < lf1; ++tl) atomicAdd(P.tile_ready + tl, 1u);
+            }
         }
     }
     // Launched programmatically behind K-sdft (which runs beside this kernel): the grid must not complete before
@@ -407,10 +421,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? PVQT_FFT_MIN_BLOCKS : (B
     if (P.n_sdft > 0 && gi == P.combine_group) {
         pdl_wait();   // the partial sums must be complete (a second wait in the last CTA is harmless)
         __syncthreads();
-        const uint32_t lf0 = (blockIdx.x - g.cta_begin) * g.frames_per_cta;
-        for (int i = 0; i < P.n_sdft; ++i)
-            sdft_combine_frames(P.sdft[i], lf0, g.frames_per_cta, fft_smem,
-                                sizeof(float2) * (size_t)pad_index(BLOCK * kPointsPerThread));
+        const uint32_t n_items = (P.frames.n_frames + g.frames_per_cta - 1) / g.frames_per_cta;
+        for (uint32_t item = blockIdx.x - g.cta_begin; item < n_items; item += (uint32_t)g.n_ctas)
+            for (int i = 0; i < P.n_sdft; ++i)
+                sdft_combine_frames(P.sdft[i], item * g.frames_per_cta, g.frames_per_cta, fft_smem,
+                                    sizeof(float2) * (size_t)pad_index(BLOCK * kPointsPerThread));
     }
 }
 

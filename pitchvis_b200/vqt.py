@@ -250,8 +250,9 @@ class Vqt:
         return int(self._lib.pvqt_launch_count(self._h))
 
     def set_fused_epilogue(self, mode: int) -> int:
-        """Tuning / test switch: 0 = unfused K-spmm + K-db, 1 = K-spmm-db one CTA per tile, 2 = cluster form
-        (default).  Returns the mode in effect (a mode the kernel does not fit falls back to a lower one)."""
+        """Tuning / test switch: 0 = unfused K-spmm + K-db, 1 = K-spmm-db one CTA per tile, 2 = cluster form,
+        3 = persistent warp-specialised pipeline (default where it fits).  Returns the mode in effect (a mode the
+        kernel does not fit falls back: 3 -> 1 -> 0)."""
         return int(self._lib.pvqt_set_fused_epilogue(self._h, int(mode)))
 
     def plan_info(self) -> dict:

@@ -39,6 +39,11 @@ __global__ void __launch_bounds__(1024) k(float *out, const float *in, int warps
             for (int i = 0; i < 8; ++i) { a[i].x += x[i & 3].x; a[i].y += x[i & 3].y; }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { a[i].x += c0.x; a[i].y += c0.y; }
+        } else if (MODE == 5) {   // FFMA2 with a scalar multiplier broadcast to both halves (the SpMM walk's actual form: R.F32)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(make_float2(c0.x, c0.x), x[i & 3], a[i]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = __ffma2_rn(make_float2(c1.y, c1.y), x[(i + 1) & 3], a[i]);
         } else if (MODE == 4) {   // FMUL2
 #pragma unroll
             for (int i = 0; i < 8; ++i) a[i] = __fmul2_rn(a[i], x[i & 3]);
@@ -84,9 +89,9 @@ int main()
     cudaMalloc(&out, (2 << 20) * sizeof(float));
     cudaMalloc(&in, 64 * sizeof(float));
     cudaMemset(in, 0, 64 * sizeof(float));
-    const char *names[] = {"FFMA2 (16/iter)", "FFMA (32/iter)", "FADD2 (16/iter)", "FADD (32/iter)", "FMUL2 (16/iter)"};
-    const int per_iter[] = {16, 32, 16, 32, 16};
-    for (int mode = 0; mode < 5; ++mode)
+    const char *names[] = {"FFMA2 (16/iter)", "FFMA (32/iter)", "FADD2 (16/iter)", "FADD (32/iter)", "FMUL2 (16/iter)", "FFMA2 bcast (16/iter)"};
+    const int per_iter[] = {16, 32, 16, 32, 16, 16};
+    for (int mode = 0; mode < 6; ++mode)
         for (int wps : {1, 2, 4, 8}) {
             const int warps = 4 * wps;
             for (int rep = 0; rep < 2; ++rep) {
@@ -96,6 +101,7 @@ int main()
                 case 2: k<2><<<148, 1024>>>(out, in, warps); break;
                 case 3: k<3><<<148, 1024>>>(out, in, warps); break;
                 case 4: k<4><<<148, 1024>>>(out, in, warps); break;
+                case 5: k<5><<<148, 1024>>>(out, in, warps); break;
                 }
                 cudaDeviceSynchronize();
             }
@@ -104,7 +110,7 @@ int main()
             // every sub-partition runs `wps` warps: cycles per warp-instruction per sub-partition
             printf("%-18s %d warps/SMSP: %.3f cycles per warp-instruction per SMSP  (%.1f lane-ops/clk/SM)\n", names[mode], wps,
                    (double)cyc / ((double)kIters * per_iter[mode] * wps),
-                   4.0 * 32.0 * (mode == 0 || mode == 2 || mode == 4 ? 2 : 1) * kIters * per_iter[mode] * wps / (double)cyc);
+                   4.0 * 32.0 * (mode == 0 || mode == 2 || mode == 4 || mode == 5 ? 2 : 1) * kIters * per_iter[mode] * wps / (double)cyc);
         }
     for (int bytes : {8, 16})
         for (int wps : {1, 2, 4, 8}) {

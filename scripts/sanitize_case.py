@@ -13,7 +13,7 @@ for mode in (1, 0, 2):                       # K-spmm-db one-CTA form, unfused p
         v.set_sliding_dft(sd)
         out = v.calculate_vqt_batch_in_db(audio, 368)
         assert np.all(np.isfinite(out)), (mode, sd)
-v.set_fused_epilogue(1); v.set_sliding_dft(2)
+v.set_fused_epilogue(3); v.set_sliding_dft(2)
 one = v.calculate_vqt_instant_in_db(audio[:v.n_fft])
 streams = np.stack([audio[:v.n_fft + 30 * 333], audio[100:100 + v.n_fft + 30 * 333]])
 v.calculate_vqt_streams_in_db(streams, 333)

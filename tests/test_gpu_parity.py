@@ -172,7 +172,7 @@ def test_spmm_db_variants_agree(vqt, oracle_default, chords):
     d_audio.upload(audio)
     res = {}
     try:
-        for mode in (2, 1, 0):
+        for mode in (3, 2, 1, 0):
             assert vqt.set_fused_epilogue(mode) == mode
             d_out = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
             d_pow = pv.DeviceBuffer(vqt, n_frames * 588 * 4)
@@ -181,13 +181,15 @@ def test_spmm_db_variants_agree(vqt, oracle_default, chords):
             pv.calc_db_device(vqt, d_audio, 1, 0, HOP, n_frames, d_out, None)  # without the optional power output
             np.testing.assert_array_equal(d_out.download((n_frames, 588)), res[mode][0])
     finally:
-        vqt.set_fused_epilogue(1)
+        vqt.set_fused_epilogue(3)
     np.testing.assert_array_equal(res[1][1], res[0][1])
     np.testing.assert_array_equal(res[1][0], res[0][0])
+    np.testing.assert_array_equal(res[3][1], res[0][1])     # the persistent pipeline form: same sums, same order
+    np.testing.assert_array_equal(res[3][0], res[0][0])
     assert _power_err_db(res[2][1], res[0][1], -60.0) <= 5e-4
     assert np.abs(res[2][0] - res[0][0]).max() <= 5e-4
     ref = oracle_default.calculate_batch_db(audio, HOP, mode=0)
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         assert np.abs(res[mode][0] - ref).max() <= TOL_DB, mode
 
 
