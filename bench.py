@@ -298,6 +298,7 @@ class Ctx:
     def __init__(self, args, rank, world, local_rank, dist):
         from pitchvis_b200 import _ffi
         self.args, self.rank, self.world, self.local_rank, self.dist = args, rank, world, local_rank, dist
+        self.cpu_group = dist.new_group(backend="gloo") if dist is not None else None
         self.lib = _ffi.load()
         self.ffi = _ffi
         self.peak, self.peak_src = measured_peak_gbs()
@@ -315,7 +316,9 @@ class Ctx:
             pv.synchronize(vqt)
         if self.dist is not None:
             import torch
-            self.dist.barrier()
+            # a host-side (gloo) barrier: an NCCL barrier is a kernel that spins on the waiting ranks' GPUs, and in the
+            # end-to-end arm rank 0 drives those very GPUs through pvqt_multi_* while the other ranks wait
+            self.dist.barrier(group=self.cpu_group)
             torch.cuda.synchronize()
 
     def reduce_max(self, *xs):
@@ -837,7 +840,7 @@ def main():
         emit(line)
 
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=ctx.cpu_group)
         dist.destroy_process_group()
 
 
