@@ -596,6 +596,10 @@ int build_fused_plan(pvqt *v)
     v->fused_capable = v->fused_ok = fused_supported(n_warps, touched_bound, (int)v->kernel.n_buckets, R);
     if (!v->fused_ok) return PVQT_OK;
 
+    // columns a unit may start early (zero coefficients) to land on a free bank-group residue: 8 makes every LDS.128 of the
+    // walk conflict-free but lengthens the walk by ~3.5 slots per unit (PVQT_CONFLICT_SHIFT)
+    int max_shift = 8;
+    if (const char *e = std::getenv("PVQT_CONFLICT_SHIFT")) max_shift = std::max(1, std::min(std::atoi(e), 8));
     std::vector<FusedWarp> warps((size_t)n_warps);
     std::vector<int4> lane_meta((size_t)n_warps * 32, make_int4(0, 0, 0, 0));
     std::vector<int2> lane_rows((size_t)n_warps * 32, make_int2(0, 0));
@@ -614,7 +618,7 @@ int build_fused_plan(pvqt *v)
         for (int i = u0; i < u1; ++i) {
             Unit &u = units[i];
             int best_q = -1, best_shift = 0;
-            for (int shift = 0; shift < 8 && best_q < 0 && u.len > 0; ++shift) {
+            for (int shift = 0; shift < max_shift && best_q < 0 && u.len > 0; ++shift) {
                 const int c = u.col0 - shift;
                 if (c < 0) break;
                 for (int q = 0; q < 4; ++q) {
@@ -716,7 +720,7 @@ int build_fused_plan(pvqt *v)
     int min_slots = 1 << 30;
     for (int w = 0; w < n_warps; ++w) min_slots = std::min(min_slots, warps[(size_t)w].width + warps[(size_t)w].nwidth);
     v->pipe_capable = pipe_supported(n_warps, P.cols_touched, P.n_buckets, R, min_slots);
-    if (v->pipe_capable && configure_pipe(n_warps, P.cols_touched, P.n_buckets, 0) != cudaSuccess) {
+    if (v->pipe_capable && configure_pipe(n_warps, P.cols_touched, P.n_buckets, 0, 0) != cudaSuccess) {
         cudaGetLastError();
         v->pipe_capable = false;
     }
@@ -1249,14 +1253,15 @@ int run_device(pvqt *v, const float *d_audio, size_t n_streams, size_t stream_st
             bool use_pipe = v->pipe_ok && v->fused_ok && !v->cluster_ok && !d_spec_out && !(v->tile_flags && !v->use_graphs && !v->capturing);
             if (use_pipe) {
                 for (const auto &sp : sd) pipe_sdft = std::max<int>(pipe_sdft, (int)pipe_sdft_floats2(sp.g.q, sp.g.nk));
-                if (pipe_smem_bytes(v->fused.cols_touched, v->fused.n_buckets, v->fused.n_warps, pipe_sdft) > 227 * 1024) {
+                const int total = pipe_sdft * (int)sd.size();   // the kernel's smem limit is raised to the largest total seen
+                if (pipe_smem_bytes(v->fused.cols_touched, v->fused.n_buckets, v->fused.n_warps, pipe_sdft, (int)sd.size()) > 227 * 1024) {
                     use_pipe = false;
-                } else if (pipe_sdft > v->pipe_sdft_configured) {
-                    if (configure_pipe(v->fused.n_warps, v->fused.cols_touched, v->fused.n_buckets, pipe_sdft) != cudaSuccess) {
+                } else if (total > v->pipe_sdft_configured) {
+                    if (configure_pipe(v->fused.n_warps, v->fused.cols_touched, v->fused.n_buckets, total, 1) != cudaSuccess) {
                         cudaGetLastError();
                         use_pipe = false;
                     } else {
-                        v->pipe_sdft_configured = pipe_sdft;
+                        v->pipe_sdft_configured = total;
                     }
                 }
             }

@@ -197,6 +197,10 @@ __global__ void __launch_bounds__(kPipeMaxThreads, 1) spmm_db_pipe_kernel(const 
             // cp.async ring of the one-CTA-per-tile form) every coefficient cost an LDS.128 and an LDGSTS -- 12 of the 28
             // cycles of the SM-wide shared-memory pipe a slot took, and that pipe, not the FMA pipe, bounded the walk
             // (profiles/r02_pipe_stats.txt).  The head of the queue is loaded before the tile's barrier: plan data only.
+            // Also measured: a warp-private ring of three 4-slot chunks filled by cp.async.bulk (lane 0 refills a chunk
+            // as soon as the warp has read it, 8-12 slots ahead): the per-chunk mbarrier wait, warp sync, proxy fence and
+            // issue cost more than the deeper prefetch gave back (walk 46.1 k cycles against 37.9 k, step 87.0 against
+            // 82.8 us).
             constexpr int kQ = 4;
             float4 kq[kQ];
 #pragma unroll
@@ -522,24 +526,24 @@ int pipe_plane_stride(int cols_touched) { return cols_touched <= 832 ? 832 : 0; 
 // float2 entries of one K-sdft group's staging: (q + 8) C rows, 8 R rows, (q + 1) phase rows, each part 16-byte aligned
 size_t pipe_sdft_floats2(int q, int nk) { return ((size_t)sd_c_cap(q, nk) + sd_r_cap(nk) + (size_t)(q + 1) * nk + 1) & ~(size_t)1; }
 
-size_t pipe_smem_bytes(int cols_touched, int n_buckets, int n_warps, int sdft_floats2)
+size_t pipe_smem_bytes(int cols_touched, int n_buckets, int n_warps, int sdft_floats2, int n_sdft)
 {
     const size_t planes = (size_t)2 * 4 * pipe_plane_stride(cols_touched) * sizeof(float4);
     const size_t ls = (size_t)2 * (((size_t)kTileFrames * n_buckets + 3) & ~(size_t)3) * sizeof(float);
     (void)n_warps;
-    return planes + ls + (size_t)kMaxSdft * sdft_floats2 * sizeof(float2);
+    return planes + ls + (size_t)std::max(0, std::min(n_sdft, kMaxSdft)) * sdft_floats2 * sizeof(float2);
 }
 
 bool pipe_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane, int min_slots)
 {
     return rows_per_lane == 2 && n_warps >= 1 && (n_warps + kPipeHelpers) * 32 <= kPipeMaxThreads &&
            pipe_plane_stride(cols_touched) > 0 && min_slots >= 1 &&
-           pipe_smem_bytes(cols_touched, n_buckets, n_warps, 0) <= 200 * 1024;
+           pipe_smem_bytes(cols_touched, n_buckets, n_warps, 0, 0) <= 200 * 1024;
 }
 
-cudaError_t configure_pipe(int n_warps, int cols_touched, int n_buckets, int sdft_floats2)
+cudaError_t configure_pipe(int n_warps, int cols_touched, int n_buckets, int sdft_floats2, int n_sdft)
 {
-    const size_t bytes = pipe_smem_bytes(cols_touched, n_buckets, n_warps, sdft_floats2);
+    const size_t bytes = pipe_smem_bytes(cols_touched, n_buckets, n_warps, sdft_floats2, n_sdft);
     if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     return cudaFuncSetAttribute(spmm_db_pipe_kernel<832>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
@@ -549,7 +553,7 @@ cudaError_t launch_spmm_db_pipe(const FusedParams &p, int n_ctas, int sdft_float
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)std::max(1, std::min<int>(n_ctas, (int)p.n_tiles)));
     cfg.blockDim = dim3((unsigned)(p.n_warps + kPipeHelpers) * 32);
-    cfg.dynamicSmemBytes = pipe_smem_bytes(p.cols_touched, p.n_buckets, p.n_warps, sdft_floats2);
+    cfg.dynamicSmemBytes = pipe_smem_bytes(p.cols_touched, p.n_buckets, p.n_warps, sdft_floats2, p.n_sdft);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

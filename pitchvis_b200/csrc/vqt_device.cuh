@@ -307,9 +307,9 @@ cudaError_t configure_fused(int n_warps, int cols_touched, int n_buckets, int ro
 // K-spmm-db, persistent warp-specialised pipeline form (spmm_pipe.cu): same FusedParams plan, one CTA per SM
 bool        pipe_supported(int n_warps, int cols_touched, int n_buckets, int rows_per_lane, int min_slots);
 int         pipe_plane_stride(int cols_touched);          // columns per plane of the scratch layout the kernel stages
-size_t      pipe_smem_bytes(int cols_touched, int n_buckets, int n_warps, int sdft_floats2);
+size_t      pipe_smem_bytes(int cols_touched, int n_buckets, int n_warps, int sdft_floats2, int n_sdft);
 size_t      pipe_sdft_floats2(int q, int nk);             // float2 entries of the combine's staging for one K-sdft group
-cudaError_t configure_pipe(int n_warps, int cols_touched, int n_buckets, int sdft_floats2);
+cudaError_t configure_pipe(int n_warps, int cols_touched, int n_buckets, int sdft_floats2, int n_sdft);
 cudaError_t launch_spmm_db_pipe(const FusedParams &p, int n_ctas, int sdft_floats2, cudaStream_t stream);
 cudaError_t configure_kernels(int max_cols);
 size_t fft_smem_bytes(int block_threads);

@@ -111,6 +111,10 @@ extern "C" {
     fn pvqt_analysis_update_vqt_smoothing_duration(a: *mut c_void, has_duration: c_int, duration_ns: u64) -> c_int;
     fn pvqt_analysis_preprocess_batch(a: *mut c_void, db: *const f32, n_buckets: usize, n_frames: usize,
                                       frame_time_ns: u64, out: *const PvqtAnalysisOutputs) -> c_int;
+    // VQT + AnalysisState in one call: the spectra stay in HBM between the transform and the epilogue
+    fn pvqt_calc_batch_analysis(v: *mut c_void, a: *mut c_void, audio: *const f32, n_samples: usize, hop: usize,
+                                n_frames: usize, frame_time_ns: u64, out: *const PvqtAnalysisOutputs, out_db: *mut f32,
+                                d2h_bytes: *mut u64) -> c_int;
 }
 
 fn last_error() -> String {
@@ -205,6 +209,55 @@ impl AnalysisState {
     pub fn preprocess(&mut self, x_vqt: &[f32], frame_time: Duration) {
         assert_eq!(x_vqt.len(), self.range.n_buckets());
         self.preprocess_batch(x_vqt, frame_time);
+    }
+
+    /// New: what every caller of the reference does per frame -- `vqt.calculate_vqt_instant_in_db(..)` then
+    /// `analysis.preprocess(..)` (pitchvis_viewer/src/vqt_system.rs:40-68 + analysis_system.rs:10-20) -- for a whole
+    /// recording in one library call: frame t = audio[t*hop .. t*hop + n_fft].  The dB spectra never leave the GPU; the
+    /// per-frame peak results come back (the public per-bin fields are not refreshed by this entry: call
+    /// `preprocess_batch` on returned spectra when they are needed).
+    pub fn calculate_and_preprocess(&mut self, vqt: &mut crate::vqt::Vqt, audio: &[f32], hop: usize,
+                                    frame_time: Duration) -> Vec<FrameAnalysis> {
+        let t = vqt.frames_in(audio.len(), hop);
+        if t == 0 {
+            return Vec::new();
+        }
+        let mut count = vec![0u32; t];
+        let mut indices = vec![0u32; t * MAX_PEAKS];
+        let mut cont = vec![ContinuousPeak::default(); t * MAX_PEAKS];
+        let mut scene = vec![0.0f32; t];
+        let mut tuning = vec![0.0f32; t];
+        let null = std::ptr::null_mut();
+        let out = PvqtAnalysisOutputs {
+            max_peaks: MAX_PEAKS as u32,
+            peak_count: count.as_mut_ptr(),
+            peak_indices: indices.as_mut_ptr(),
+            peaks_continuous: cont.as_mut_ptr(),
+            x_vqt_smoothed: null, x_vqt_peakfiltered: null, x_vqt_afterglow: null, calmness: null,
+            pitch_accuracy: null, pitch_deviation: null,
+            smoothed_scene_calmness: scene.as_mut_ptr(),
+            smoothed_tuning_grid_inaccuracy: tuning.as_mut_ptr(),
+        };
+        let rc = unsafe {
+            pvqt_calc_batch_analysis(vqt.raw_handle(), self.handle, audio.as_ptr(), audio.len(), hop, t,
+                                     frame_time.as_nanos() as u64, &out, std::ptr::null_mut(), std::ptr::null_mut())
+        };
+        assert!(rc == PVQT_OK, "pvqt_calc_batch_analysis failed: {}", last_error());
+        let frames: Vec<FrameAnalysis> = (0..t).map(|f| {
+            let c = (count[f] as usize).min(MAX_PEAKS);
+            FrameAnalysis {
+                peaks: indices[f * MAX_PEAKS..f * MAX_PEAKS + c].iter().map(|&i| i as usize).collect(),
+                peaks_continuous: cont[f * MAX_PEAKS..f * MAX_PEAKS + c].to_vec(),
+                smoothed_scene_calmness: scene[f],
+                smoothed_tuning_grid_inaccuracy: tuning[f],
+            }
+        }).collect();
+        let last = &frames[t - 1];
+        self.peaks = last.peaks.iter().copied().collect();
+        self.peaks_continuous = last.peaks_continuous.clone();
+        self.smoothed_scene_calmness.y = last.smoothed_scene_calmness;
+        self.smoothed_tuning_grid_inaccuracy.y = last.smoothed_tuning_grid_inaccuracy;
+        frames
     }
 
     /// New: `db` holds T consecutive frames (frame-major).  The public fields hold the state after the last

@@ -136,6 +136,7 @@ const PVQT_BAD_LENGTH: c_int = 4;
 
 #[link(name = "pvqt")]
 extern "C" {
+    fn pvqt_set_log_callback(f: Option<extern "C" fn(c_int, *const c_char, *mut c_void)>, user: *mut c_void, max_level: c_int) -> c_int;
     fn pvqt_last_error_string() -> *const c_char;
     fn pvqt_create(params: *const PvqtParams, device: c_int, out: *mut *mut c_void, err: *mut PvqtError) -> c_int;
     fn pvqt_destroy(v: *mut c_void);
@@ -184,6 +185,16 @@ unsafe fn csmat(v: &PvqtCsrView) -> sprs::CsMat<Complex32> {
 impl Vqt {
     /// `Vqt::new` on CUDA device 0 (`PVQT_DEVICE` selects another one).
     pub fn new(params: &VqtParameters) -> Result<Self, VqtError> {
+        // the reference logs through the `log` crate (vqt.rs:468, :661-667, :688-710, :741-746): forward the library's lines
+        extern "C" fn sink(level: c_int, message: *const c_char, _user: *mut c_void) {
+            let m = unsafe { CStr::from_ptr(message) }.to_string_lossy();
+            match level {
+                1 => log::warn!("{m}"),
+                2 => log::info!("{m}"),
+                _ => log::debug!("{m}"),
+            }
+        }
+        unsafe { pvqt_set_log_callback(Some(sink), std::ptr::null_mut(), 3) };
         let device = std::env::var("PVQT_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
         Self::new_on_device(params, device)
     }
@@ -233,6 +244,15 @@ impl Vqt {
         let delay = Duration::from_secs_f32(unsafe { pvqt_delay_seconds(handle) } as f32);
         log::info!("VQT analysis delay: {} ms.", delay.as_millis());
         Ok(Self { params: params.clone(), vqt_kernel: VqtKernel { window_groups }, delay, handle })
+    }
+
+    /// The C handle, for entries that take a `Vqt` and an `AnalysisState` (analysis::calculate_and_preprocess).
+    pub(crate) fn raw_handle(&mut self) -> *mut c_void {
+        self.handle
+    }
+
+    pub fn frames_in(&self, n_samples: usize, hop: usize) -> usize {
+        unsafe { pvqt_frames_in(self.handle, n_samples, hop) }
     }
 
     pub fn params(&self) -> &VqtParameters {
