@@ -157,6 +157,7 @@ __host__ __device__ constexpr int plan_radix(int nc, int pass)
 // pad_index(i + m) == pad_index(i) + m + m / 16 whenever m is a multiple of 16, which turns the
 // per-point index arithmetic of a pass into compile-time offsets from one base pointer.
 __host__ __device__ constexpr int pad_index(int i) { return i + (i >> 4); }
+constexpr int kEdgeSlot = 16;   // a padding slot of every FFT buffer (N_c >= 32)
 
 // Barrier among the T threads that share one FFT (several FFTs share a CTA when T < BLOCK).
 // The barrier id must be an immediate: with `bar.sync %r, T` ptxas reserves all 16 named barriers for the CTA, and
@@ -273,7 +274,8 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             }
         }
     }
-    fft_sync<T, BLOCK>(fid);
+    if constexpr (kLast) __syncthreads();   // the split step reads the buffers of every frame of the CTA
+    else fft_sync<T, BLOCK>(fid);
 
     if constexpr (!kLast) fft_passes<NC, PASS + 1, NS * R, BLOCK>(v, s, t, fid, x, valid, g);
 }
@@ -316,40 +318,78 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
 #else
     const bool shifted = false;
 #endif
-    float edge = 0.f;
     if (shifted) {
         x -= 1;
-        if (valid) edge = __ldg(x + 2 * NC) - __ldg(x);
+        // the frame's edge term, parked in a padding slot of its buffer (pad_index() never maps to 16) for the split step
+        if (t == 0) s[kEdgeSlot] = make_float2(valid ? __ldg(x + 2 * NC) - __ldg(x) : 0.f, 0.f);
     }
 
     float2 v[kPointsPerThread];
-    fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g);
+    fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g);   // ends with a CTA-wide barrier
 
     // Real-FFT split: with Z = FFT_{NC}(z), E/O the spectra of the even/odd samples,
     //   X[c] = E[c] + W_N^c O[c],  E = (Z[c] + conj Z[NC-c]) / 2,  O = -i (Z[c] - conj Z[NC-c]) / 2
-    // written straight into the tiled spectrum layout the SpMM stages (spec_index()).
-    if (valid) {
+    // written straight into the spectrum layout K-spmm-db stages.  The CTA's FPC frames are consecutive frames of one
+    // tile, so the step runs over (column, group of VEC frames): the twiddle and the index arithmetic are shared by the
+    // VEC frames and each thread stores whole 4-frame chunks (16 bytes; 8 when a CTA holds two frames) -- a quarter
+    // of the instructions of one thread per (column, frame), which at the defaults were a quarter of the kernel's
+    // (profiles/r02_d_fft_sass_segments.txt).  Frames past the end of the launch transformed zeros: their chunks
+    // are zeros, inside the last tile of the scratch.
+    {
+        constexpr int VEC = FPC >= 4 ? 4 : FPC;    // frames per store
+        constexpr int NV = FPC / VEC;              // frame groups per column
+        constexpr int PAD = pad_index(NC);
+        const uint32_t lf0 = item * FPC;
         const int n_cols = g.col_hi - g.col_lo + 1;
-        for (int i = t; i < n_cols; i += T) {
-            const int c = g.col_lo + i;
-            const float2 zk = s[pad_index(c & (NC - 1))];
-            const float2 zn = s[pad_index((NC - c) & (NC - 1))];
-            const float2 e = __fmul2_rn(__fadd2_rn(zk, make_float2(zn.x, -zn.y)), make_float2(0.5f, 0.5f));
-            const float2 d = __fmul2_rn(__fadd2_rn(zk, make_float2(-zn.x, zn.y)), make_float2(0.5f, 0.5f));
-            const float2 o = cmul_mi(d);
+        const bool planes = P.plane_stride > 0;
+        for (int idx = tid; idx < n_cols * NV; idx += BLOCK) {
+            int vg = 0, i = idx;
+            if constexpr (NV > 1) { vg = idx / n_cols; i = idx - vg * n_cols; }
+            const int c = g.col_lo + i, col = g.spec_offset + i;
+            const float2 *zk_p = smem + vg * (VEC * PAD) + pad_index(c & (NC - 1));
+            const float2 *zn_p = smem + vg * (VEC * PAD) + pad_index((NC - c) & (NC - 1));
+            const float2 *edge_p = smem + vg * (VEC * PAD) + kEdgeSlot;
             const float2 w = __ldg(g.split_twiddle + i);
-            float2 xc = cadd(e, cmul(o, w));
-            if (shifted) xc = cmul(make_float2(xc.x + edge, xc.y), make_float2(w.x, -w.y));   // W^-c = conj(w)
-            if (P.plane_stride > 0) {
-                P.spec[plane_index(local_frame, g.spec_offset + i, P.plane_stride, 0)] = xc.x;
-                P.spec[plane_index(local_frame, g.spec_offset + i, P.plane_stride, 1)] = xc.y;
+            float xre[VEC], xim[VEC];
+#pragma unroll
+            for (int f = 0; f < VEC; ++f) {
+                const float2 zk = zk_p[f * PAD], zn = zn_p[f * PAD];
+                const float2 e = __fmul2_rn(__fadd2_rn(zk, make_float2(zn.x, -zn.y)), make_float2(0.5f, 0.5f));
+                const float2 d = __fmul2_rn(__fadd2_rn(zk, make_float2(-zn.x, zn.y)), make_float2(0.5f, 0.5f));
+                const float2 o = cmul_mi(d);
+                float2 xc = cadd(e, cmul(o, w));
+                if (shifted) xc = cmul(make_float2(xc.x + edge_p[f * PAD].x, xc.y), make_float2(w.x, -w.y));   // W^-c = conj(w)
+                xre[f] = xc.x;
+                xim[f] = xc.y;
+            }
+            // first frame of the group: a multiple of VEC, so the group lies in one half of one tile
+            const uint32_t lf = lf0 + (uint32_t)(vg * VEC), tile = lf / kTileFrames;
+            const int f0 = (int)(lf % kTileFrames), half = f0 >> 2;
+            float *re_p, *im_p;
+            if (planes) {   // [tile][chunk][column][4]: chunk = half (Re), 2 + half (Im)
+                re_p = P.spec + (((size_t)tile * 4 + half) * P.plane_stride + col) * 4 + (f0 & 3);
+                im_p = re_p + (size_t)2 * P.plane_stride * 4;
+            } else {        // [tile][column][4 swizzled chunks][4], spec_index_re / _im
+                const int sw = (col >> 1) & 3;
+                float *rec = P.spec + ((size_t)tile * P.spec_stride + col) * (2 * kTileFrames) + (f0 & 3);
+                re_p = rec + ((half ^ sw) << 2);
+                im_p = rec + (((2 + half) ^ sw) << 2);
+            }
+            if constexpr (VEC == 4) {
+                *reinterpret_cast<float4 *>(re_p) = make_float4(xre[0], xre[1], xre[2], xre[3]);
+                *reinterpret_cast<float4 *>(im_p) = make_float4(xim[0], xim[1], xim[2], xim[3]);
+            } else if constexpr (VEC == 2) {
+                *reinterpret_cast<float2 *>(re_p) = make_float2(xre[0], xre[1]);
+                *reinterpret_cast<float2 *>(im_p) = make_float2(xim[0], xim[1]);
             } else {
-                P.spec[spec_index_re(local_frame, g.spec_offset + i, P.spec_stride)] = xc.x;
-                P.spec[spec_index_im(local_frame, g.spec_offset + i, P.spec_stride)] = xc.y;
+                if (valid) {   // one frame per CTA: nothing to pad
+                    *re_p = xre[0];
+                    *im_p = xim[0];
+                }
             }
         }
     }
-    fft_sync<T, BLOCK>(fid);   // the next item's first pass overwrites the buffer the split step has just read
+    __syncthreads();   // the next item's first pass overwrites the buffers the split step has just read
     }
 }
 
