@@ -43,6 +43,14 @@ cudaError_t read_phase_stamps(unsigned long long *out) { return cudaMemcpyFromSy
 #else
 #define PVQT_STAMP(kernel, slot) do { } while (0)
 #endif
+#ifdef PVQT_FFT_STATS
+// Diagnostic build only (scripts/fft_stats.py): cycles thread 0 of every CTA spends per phase of its work item, summed
+// per FFT size.  A stamp taken right after a barrier or a load is its ISSUE time: the wait shows up in the next phase.
+__device__ unsigned long long g_fft_stats[16][16];   // [log2 N_c][phase]; phase 15 = CTAs
+#define FFT_T(slot) do { if (threadIdx.x == 0) fft_t[slot] = clock64(); } while (0)
+#else
+#define FFT_T(slot) do { } while (0)
+#endif
 namespace {
 
 constexpr float kSqrtHalf = 0.70710678118654752440f;
@@ -191,8 +199,9 @@ __device__ __forceinline__ void fft_sync(int fid)
 //     out[(b - k) R + k + r NS] = DFT_R(v)[r]
 template <int NC, int PASS, int NS, int BLOCK>
 __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2 *s, int t, int fid, const float *x,
-                                           bool valid, const FftGroup &g)
+                                           bool valid, const FftGroup &g, long long *fft_t, bool shifted, float2 &aux)
 {
+    (void)fft_t;
     constexpr int R = plan_radix(NC, PASS);
     constexpr int T = NC / kPointsPerThread;
     constexpr int NB = kPointsPerThread / R;
@@ -238,6 +247,7 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             }
         }
     }
+    FFT_T(1 + 3 * PASS);   // loads issued
     if constexpr (!kFirst) fft_sync<T, BLOCK>(fid);  // all reads done before the in-place overwrite
 
 #pragma unroll
@@ -274,10 +284,20 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             }
         }
     }
+    if constexpr (kFirst) {
+        // the frame's edge term (loaded by the caller before the window, used only here: its latency hides behind the
+        // first pass), parked in a padding slot of the frame's buffer for the split step
+        if (shifted && t == 0) s[kEdgeSlot] = make_float2(aux.x - aux.y, 0.f);
+    }
+    if constexpr (kLast) {   // the split step's first twiddle, in flight across the barrier
+        aux = (int)threadIdx.x <= g.col_hi - g.col_lo ? __ldg(g.split_twiddle + threadIdx.x) : make_float2(0.f, 0.f);
+    }
+    FFT_T(2 + 3 * PASS);   // butterflies and stores issued
     if constexpr (kLast) __syncthreads();   // the split step reads the buffers of every frame of the CTA
     else fft_sync<T, BLOCK>(fid);
+    FFT_T(3 + 3 * PASS);   // barrier issued
 
-    if constexpr (!kLast) fft_passes<NC, PASS + 1, NS * R, BLOCK>(v, s, t, fid, x, valid, g);
+    if constexpr (!kLast) fft_passes<NC, PASS + 1, NS * R, BLOCK>(v, s, t, fid, x, valid, g, fft_t, shifted, aux);
 }
 
 template <int NC, int BLOCK>
@@ -293,6 +313,13 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
     // One wave of CTAs: CTA c of the group transforms the frames of work items c, c + n_ctas, ... (an item = FPC frames),
     // so that every SM finishes at about the same time instead of a last, mostly empty wave of one-item CTAs.
     const uint32_t n_items = (P.frames.n_frames + FPC - 1) / FPC;
+#ifdef PVQT_FFT_STATS
+    long long fft_t[14];
+    for (auto &q : fft_t) q = 0;
+    const long long t_cta = clock64();
+#else
+    long long *fft_t = nullptr;
+#endif
 #pragma unroll 1
     for (uint32_t item = blockIdx.x - g.cta_begin; item < n_items; item += (uint32_t)g.n_ctas) {
     const uint32_t local_frame = item * FPC + fid;
@@ -318,14 +345,15 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
 #else
     const bool shifted = false;
 #endif
+    float2 aux = make_float2(0.f, 0.f);   // in: the two samples of the edge term; out: the split step's first twiddle
     if (shifted) {
         x -= 1;
-        // the frame's edge term, parked in a padding slot of its buffer (pad_index() never maps to 16) for the split step
-        if (t == 0) s[kEdgeSlot] = make_float2(valid ? __ldg(x + 2 * NC) - __ldg(x) : 0.f, 0.f);
+        if (t == 0 && valid) aux = make_float2(__ldg(x + 2 * NC), __ldg(x));
     }
 
     float2 v[kPointsPerThread];
-    fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g);   // ends with a CTA-wide barrier
+    FFT_T(0);
+    fft_passes<NC, 0, 1, BLOCK>(v, s, t, fid, x, valid, g, fft_t, shifted, aux);   // ends with a CTA-wide barrier
 
     // Real-FFT split: with Z = FFT_{NC}(z), E/O the spectra of the even/odd samples,
     //   X[c] = E[c] + W_N^c O[c],  E = (Z[c] + conj Z[NC-c]) / 2,  O = -i (Z[c] - conj Z[NC-c]) / 2
@@ -349,7 +377,7 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
             const float2 *zk_p = smem + vg * (VEC * PAD) + pad_index(c & (NC - 1));
             const float2 *zn_p = smem + vg * (VEC * PAD) + pad_index((NC - c) & (NC - 1));
             const float2 *edge_p = smem + vg * (VEC * PAD) + kEdgeSlot;
-            const float2 w = __ldg(g.split_twiddle + i);
+            const float2 w = idx == tid && tid < n_cols ? aux : __ldg(g.split_twiddle + i);
             float xre[VEC], xim[VEC];
 #pragma unroll
             for (int f = 0; f < VEC; ++f) {
@@ -389,7 +417,24 @@ __device__ __forceinline__ void fft_group_body(const FftParams &P, const FftGrou
             }
         }
     }
+    FFT_T(13);   // split step issued
     __syncthreads();   // the next item's first pass overwrites the buffers the split step has just read
+#ifdef PVQT_FFT_STATS
+    if (threadIdx.x == 0) {
+        constexpr int L2 = NC == 32 ? 5 : NC == 64 ? 6 : NC == 128 ? 7 : NC == 256 ? 8 : NC == 512 ? 9 : NC == 1024 ? 10 : NC == 2048 ? 11 : NC == 4096 ? 12 : NC == 8192 ? 13 : 14;
+        const long long t_end = clock64();
+        long long prev = t_cta;
+        atomicAdd(&g_fft_stats[L2][0], (unsigned long long)(fft_t[0] - t_cta));   // item addressing, edge
+        prev = fft_t[0];
+        for (int q = 1; q <= 13; ++q) {
+            if (fft_t[q] == 0) continue;
+            atomicAdd(&g_fft_stats[L2][q], (unsigned long long)(fft_t[q] - prev));
+            prev = fft_t[q];
+        }
+        atomicAdd(&g_fft_stats[L2][14], (unsigned long long)(t_end - prev));      // last barrier
+        atomicAdd(&g_fft_stats[L2][15], 1ull);
+    }
+#endif
     }
 }
 
@@ -1037,3 +1082,16 @@ cudaError_t launch_power_to_db(const DbParams &p, cudaStream_t stream)
 }
 
 }  // namespace pvqt_dev
+
+#ifdef PVQT_FFT_STATS
+extern "C" int pvqt_debug_fft_stats(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, pvqt_dev::g_fft_stats, sizeof(pvqt_dev::g_fft_stats)) != cudaSuccess) return 7;
+    if (reset) {
+        static unsigned long long zeros[16][16] = {};
+        cudaMemcpyToSymbol(pvqt_dev::g_fft_stats, zeros, sizeof(zeros));
+    }
+    return 0;
+}
+#endif
