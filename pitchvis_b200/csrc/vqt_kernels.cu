@@ -57,6 +57,31 @@ constexpr float kSqrtHalf = 0.70710678118654752440f;
 constexpr float kCosPi8 = 0.92387953251128675613f;
 constexpr float kSinPi8 = 0.38268343236508977173f;
 
+// L1 policy of K-fft's two kinds of read-only loads: the audio of a work item is read once per CTA (the overlap of neighbouring
+// frames is served by L2: they run on other SMs), the twiddle tables by every CTA of the SM.
+__device__ __forceinline__ float2 ld_audio2(const float2 *p)
+{
+#if defined(PVQT_FFT_L1_HINTS)
+    float2 v;
+    asm volatile("ld.global.nc.L1::evict_first.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#elif defined(PVQT_FFT_AUDIO_CG)
+    return __ldcg(p);
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ float2 ld_twiddle(const float2 *p)
+{
+#if defined(PVQT_FFT_L1_HINTS)
+    float2 v;
+    asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // multiply by W16^M = exp(-2 pi i M / 16), M compile-time
 template <int M>
 __device__ __forceinline__ float2 mul_w16(float2 a)
@@ -229,7 +254,7 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             if ((reinterpret_cast<uintptr_t>(x) & 7) == 0) {  // even window start: one 8-byte load per point
 #pragma unroll
                 for (int r = 0; r < R; ++r)
-                    v[i * R + r] = valid ? __ldg(reinterpret_cast<const float2 *>(xb) + r * LD) : make_float2(0.f, 0.f);
+                    v[i * R + r] = valid ? ld_audio2(reinterpret_cast<const float2 *>(xb) + r * LD) : make_float2(0.f, 0.f);
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r)
@@ -258,7 +283,7 @@ __device__ __forceinline__ void fft_passes(float2 (&v)[kPointsPerThread], float2
             const int k = b & (NS - 1);
             const float2 *tw = g.twiddle[PASS] + k;
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[i * R + r] = cmul(v[i * R + r], __ldg(tw + (r - 1) * NS));
+            for (int r = 1; r < R; ++r) v[i * R + r] = cmul(v[i * R + r], ld_twiddle(tw + (r - 1) * NS));
         }
         butterfly<R>(&v[i * R]);
 
