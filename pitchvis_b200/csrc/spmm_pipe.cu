@@ -94,7 +94,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 #ifdef PVQT_PIPE_STATS
 // Diagnostic build only (scripts/pipe_stats.py): cycles lane 0 of walker warp 0 / helper warp 0 spends per phase.
-#define PIPE_T(var) const long long var = clock64()
+// The stamp reads shared memory first: a plain clock read after BAR.SYNC.DEFER_BLOCKING issues before the barrier
+// completes (the wait would be booked on the next phase); a memory access cannot.
+#define PIPE_T(var)                                                                                            \
+    long long var;                                                                                            \
+    {                                                                                                         \
+        unsigned d_;                                                                                          \
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d_) : "r"(smem_addr(&mbar[0])) : "memory");   \
+        var = clock64() + (long long)(d_ & 0u);                                                               \
+    }
 #define PIPE_ACC(slot, t0, t1) do { if (lane == 0 && (warp == 0 || warp == nw) && blockIdx.x < 256) g_pipe_stats[blockIdx.x][slot] += (t1) - (t0); } while (0)
 #else
 #define PIPE_T(var) do { } while (0)
