@@ -37,7 +37,7 @@ int acuda(cudaError_t e, const char *what)
         if (_e != cudaSuccess) return acuda(_e, #call);       \
     } while (0)
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // 12 warps: three search groups of four
 constexpr int kMaxPeaksSmem = 256;  // peaks of one frame kept in shared memory (588 bins, distance 3 -> <= 196)
 
 struct AnalysisKernelParams {
@@ -51,6 +51,16 @@ struct AnalysisKernelParams {
     uint64_t frame_time_ns;
     pvqt_analysis_outputs out;   // device pointers
 };
+
+#ifdef PVQT_ANALYSIS_STATS
+// Diagnostic build only (scripts/analysis_stats.py): cycles thread 0 of CTA 0 spends per phase of a frame, summed over the frames.
+__device__ unsigned long long g_analysis_stats[16];
+#define A_T(var) const long long var = clock64()
+#define A_ACC(slot, t0, t1) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_analysis_stats[slot] += (unsigned long long)((t1) - (t0)); } while (0)
+#else
+#define A_T(var) do { } while (0)
+#define A_ACC(slot, t0, t1) do { } while (0)
+#endif
 
 // ---- std::time::Duration / EmaMeasurement -------------------------------------------------------
 __host__ __device__ inline float dur_as_secs_f32(uint64_t ns)
@@ -84,27 +94,57 @@ __device__ __forceinline__ float ema_step(float y, float alpha, float x) { retur
 // ---- cooperative peak search (find_peaks wrapper, peak_detection.rs:26-51) -------------------------
 enum : unsigned char { kNone = 0, kUndecided = 1, kKept = 2, kRemoved = 3 };
 
-// st[b] = 1 for every peak of x[0..n), else 0.  All threads of the CTA must call.
-__device__ void find_peaks_block(const float *x, int n, float min_prominence, float min_height, int distance,
-                                 int min_bin, unsigned char *st)
+// Barrier among the `count` threads (a multiple of 32) of one search group; id 1..15.
+__device__ __forceinline__ void group_sync(int id, int count)
 {
-    const int tid = threadIdx.x;
-    for (int b = tid; b < n; b += kThreads) st[b] = kNone;
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool group_sync_or(int id, int count, bool pred)
+{
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(count), "r"((unsigned)pred) : "memory");
+    return r != 0;
+}
+
+__device__ __forceinline__ void st_out(unsigned char *st, int b, unsigned char v) { st[b] = v; }
+
+// st[b] = 1 for every peak of x[0..n), else 0.  Called by the gsz threads (whole warps, gtid = 0..gsz-1) of one search
+// group, which synchronise on named barrier `bar`: the three searches of a frame run side by side on three groups of
+// warps -- each search is a chain of short, latency-bound phases, so a third of the CTA finishes one nearly as fast as
+// the whole CTA did (10 k cycles each, one after the other, before: profiles/r02_f_analysis_phase_cycles.txt).
+__device__ void find_peaks_group(const float *x, int n, float min_prominence, float min_height, int distance,
+                                 int min_bin, unsigned char *st, int gtid, int gsz, int bar, float *warp_min)
+{
+    A_T(p0);
+    // (also the minimum of x: a peak lower than min_prominence above it cannot pass, whatever its surroundings)
+    float lo_x = CUDART_INF_F;
+    for (int b = gtid; b < n; b += gsz) {
+        st[b] = kNone;
+        lo_x = fminf(lo_x, x[b]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+    if ((gtid & 31) == 0) warp_min[gtid >> 5] = lo_x;
+    group_sync(bar, gsz);
+    float x_min = warp_min[0];
+    for (int w = 1; w < (gsz >> 5); ++w) x_min = fminf(x_min, warp_min[w]);
     // strict local maxima, plateaus at their middle, then min_height
-    for (int b = tid + 1; b < n - 1; b += kThreads) {
+    for (int b = gtid + 1; b < n - 1; b += gsz) {
         if (x[b - 1] < x[b]) {
             int ahead = b + 1;
             while (ahead < n - 1 && x[ahead] == x[b]) ++ahead;
             if (x[ahead] < x[b] && x[b] >= min_height) st[(b + ahead - 1) >> 1] = kUndecided;
         }
     }
-    __syncthreads();
+    group_sync(bar, gsz);
+    A_T(p1);
+    A_ACC(8, p0, p1);
     // min_distance: taller peaks win (greedy by height == repeated "local champion" rounds)
     if (distance > 1) {
-        int pending;
+        bool pending;
         do {
-            for (int b = tid; b < n; b += kThreads) {
+            for (int b = gtid; b < n; b += gsz) {
                 if (st[b] != kUndecided) continue;
                 bool has_kept = false, top = true;
                 const int lo = max(b - distance + 1, 0), hi = min(b + distance - 1, n - 1);
@@ -116,61 +156,51 @@ __device__ void find_peaks_block(const float *x, int n, float min_prominence, fl
                 }
                 if (!has_kept && top) st[b] = kKept;
             }
-            __syncthreads();
-            pending = 0;
-            for (int b = tid; b < n; b += kThreads) {
+            group_sync(bar, gsz);
+            pending = false;
+            for (int b = gtid; b < n; b += gsz) {
                 if (st[b] != kUndecided) continue;
                 bool has_kept = false;
                 const int lo = max(b - distance + 1, 0), hi = min(b + distance - 1, n - 1);
                 for (int j = lo; j <= hi; ++j) has_kept |= (j != b && st[j] == kKept);
                 if (has_kept) st[b] = kRemoved;
-                else pending = 1;
+                else pending = true;
             }
-            pending = __syncthreads_or(pending);
+            pending = group_sync_or(bar, gsz, pending);
         } while (pending);
     } else {
-        for (int b = tid; b < n; b += kThreads) if (st[b] == kUndecided) st[b] = kKept;
-        __syncthreads();
+        for (int b = gtid; b < n; b += gsz) if (st[b] == kUndecided) st[b] = kKept;
+        group_sync(bar, gsz);
     }
-    // min_prominence, then drop the lowest half semitone.  The bases of a peak are the minima of the stretches to its
-    // left and right over which nothing is higher (the walk stops at the first x[i] > h): for the tallest peaks those
-    // stretches span the whole spectrum, and a thread walking them alone (one dependent shared-memory load per step) cost
-    // 9 us per side and call.  A warp walks a peak's stretch 32 bins at a time instead: ballot for the first higher
-    // bin, min over the lanes before it.  min is exact whatever the order, so the result is the sequential walk's.
-    const int lane = tid & 31;
-    for (int b0 = (tid & ~31); b0 < n; b0 += kThreads) {       // the warp's 32 consecutive bins of this round
-        const int b = b0 + lane;
-        const bool kept = b < n && st[b] == kKept;
-        unsigned todo = __ballot_sync(0xffffffffu, kept);
-        unsigned char r = 0;
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int p = b0 + src;
-            const float h = x[p];
-            float mins[2];
+    A_T(p2);
+    A_ACC(9, p1, p2);
+    // min_prominence, then drop the lowest half semitone.  A peak's prominence is its height over the higher of its two
+    // bases, a base being the minimum of the stretch to that side over which nothing is higher than the peak.  Only the
+    // comparison with min_prominence is needed, and f32 subtraction is monotonic, so
+    //     h - max(base_l, base_r) >= P   <=>   on EACH side some bin with h - x[i] >= P comes before the first x[i] > h
+    // and the walk of a side ends at the first bin that decides it -- a few bins for a narrow spectral peak, however
+    // tall (walking the whole stretch of the tallest peaks, 32 bins at a time by a warp, cost 3.6-8.5 k cycles per
+    // search).  One thread per kept bin, its own two short walks.
+    for (int b = gtid; b < n; b += gsz) {
+        if (st[b] != kKept) { st_out(st, b, 0); continue; }
+        const float h = x[b];
+        // every bin is >= x_min and f32 subtraction is monotonic: h - x[i] <= h - x_min < P on both sides
+        bool ok = b >= min_bin && h - x_min >= min_prominence;
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                float m = h;
-                for (int base = p;; base += side ? 32 : -32) {
-                    const int i = side ? base + lane : base - lane;
-                    const bool in = side ? i < n : i >= 0;
-                    const float v = in ? x[i] : h;
-                    const unsigned stop = __ballot_sync(0xffffffffu, in && !(v <= h));   // first bin that is higher (or NaN)
-                    const int first = stop ? __ffs(stop) - 1 : 32;
-                    if (in && lane < first) m = fminf(m, v);
-                    const bool more = side ? base + 32 < n : base - 32 >= 0;
-                    if (stop || !more) break;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                mins[side] = m;
+        for (int side = 0; side < 2 && ok; ++side) {
+            bool deep = false;
+            for (int i = side ? b + 1 : b - 1; side ? i < n : i >= 0; side ? ++i : --i) {
+                const float v = x[i];
+                if (!(v <= h)) break;                       // a higher bin (or NaN) ends the stretch
+                if (h - v >= min_prominence) { deep = true; break; }
             }
-            if (lane == src) r = (h - fmaxf(mins[0], mins[1]) >= min_prominence && p >= min_bin) ? 1 : 0;
+            // (the peak itself belongs to the stretch: h - h >= P only for P <= 0)
+            ok = deep || (h - h >= min_prominence);
         }
-        if (b < n) st[b] = r;
+        st_out(st, b, ok ? 1 : 0);
     }
-    __syncthreads();
+    A_T(p3);
+    A_ACC(10, p2, p3);
 }
 
 __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constant__ AnalysisKernelParams P)
@@ -179,14 +209,18 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
     const int n = P.nb, tid = threadIdx.x, stream = blockIdx.x;
     float *xraw = reinterpret_cast<float *>(a_smem);
     float *sm = xraw + n, *calm = sm + n, *released = calm + n, *aglow = released + n, *termc = aglow + n,
-          *termw = termc + n, *pacc = termw + n, *pdev = pacc + n;
-    float2 *pk_cont = reinterpret_cast<float2 *>(pdev + n);
+          *termw = termc + n, *pacc = termw + n, *pdev = pacc + n, *logf_bin = pdev + n;
+    float2 *pk_cont = reinterpret_cast<float2 *>(logf_bin + n);
     float *pk_power = reinterpret_cast<float *>(pk_cont + kMaxPeaksSmem);
-    int *pk_idx = reinterpret_cast<int *>(pk_power + kMaxPeaksSmem);
+    float *pk_dev = pk_power + kMaxPeaksSmem;                 // deviation from the semitone grid, its |.| * power, the rounded bin
+    float *pk_inacc = pk_dev + kMaxPeaksSmem;
+    int *pk_bin = reinterpret_cast<int *>(pk_inacc + kMaxPeaksSmem);
+    int *pk_idx = pk_bin + kMaxPeaksSmem;
     int *scan = pk_idx + kMaxPeaksSmem;                       // kThreads + 1
     unsigned char *st_bass = reinterpret_cast<unsigned char *>(scan + kThreads + 2);
     unsigned char *st_gen = st_bass + n, *st_raw = st_gen + n;
-    __shared__ float s_scene, s_tuning;
+    __shared__ float s_scene, s_tuning, s_wc, s_ws;
+    __shared__ float s_warp_min[kThreads / 32];
     __shared__ int s_npeaks;
 
     const size_t so = (size_t)stream * n;
@@ -196,6 +230,8 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
         released[b] = P.st_released[so + b];
         aglow[b] = P.st_afterglow[so + b];
     }
+    // ln of every bin's centre frequency (peak_detection.rs:79-85 evaluates it per peak and frame; it depends on the bin only)
+    for (int b = tid; b < n; b += kThreads) logf_bin[b] = cr_logf(P.min_freq * cr_powf(2.0f, (float)b / (float)P.bpo));
     if (tid == 0) { s_scene = P.st_scalar[2 * stream]; s_tuning = P.st_scalar[2 * stream + 1]; }
     __syncthreads();
 
@@ -212,39 +248,96 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
     const int hb = prm.highest_bassnote > 0x7fffffffull ? 0x7fffffff : (int)prm.highest_bassnote;
     const int chunk = (n + kThreads - 1) / kThreads;
 
+    // alpha of a bin's EMA changes only when its horizon, truncated to whole milliseconds, does: a thread keeps the last
+    // (milliseconds, alpha) of its bins in registers and evaluates the f64 exp only on a change (scene calmness drifts
+    // slowly: a few bins per frame instead of all of them)
+    constexpr int kBinsPerThread = 8;                     // n <= kBinsPerThread * kThreads uses the cache
+    uint64_t ema_ms[kBinsPerThread];
+    float ema_a[kBinsPerThread];
+#pragma unroll
+    for (int k = 0; k < kBinsPerThread; ++k) { ema_ms[k] = ~0ull; ema_a[k] = 0.0f; }
+    const bool ema_cached = n <= kBinsPerThread * kThreads;
+    float x_next[kBinsPerThread];
+#pragma unroll
+    for (int k = 0; k < kBinsPerThread; ++k) {
+        const int b = tid + k * kThreads;
+        x_next[k] = (b < n && P.n_frames > 0) ? P.db[(size_t)stream * P.n_frames * n + b] : 0.0f;
+    }
+
     for (uint32_t t = 0; t < P.n_frames; ++t) {
         const size_t fo = ((size_t)stream * P.n_frames + t);
         const float *x = P.db + fo * n;
+        A_T(a0);
         // ---- calmness-adaptive EMA of the dB spectrum (analysis.rs:295-329) -----------------------
         const float calmness_multiplier =
             prm.vqt_smoothing_calmness_min + (prm.vqt_smoothing_calmness_max - prm.vqt_smoothing_calmness_min) * s_scene;
-        for (int b = tid; b < n; b += kThreads) {
-            const float xv = x[b];
+#pragma unroll
+        for (int k = 0; k < kBinsPerThread; ++k) {
+            const int b = tid + k * kThreads;
+            if (b >= n) break;
+            const float xv = x_next[k];          // loaded one frame ahead (below): an L2 round trip off the frame's critical path
+            if (t + 1 < P.n_frames) x_next[k] = x[(size_t)n + b];
             xraw[b] = xv;
             float y = sm[b];
             if (!P.has_horizon) {
                 y = xv;                                                           // util.rs:117-120
             } else {
-                uint64_t horizon_ns = 0;                                          // base 0 ms: horizon stays 0 ms
+                uint64_t horizon_ms = 0;                                          // base 0 ms: horizon stays 0 ms
                 if (base_ms > 0) {
                     const float octave_fraction = (float)b / bpo_f / (float)P.octaves;
                     const float frequency_multiplier = 1.5f - 0.5f * octave_fraction;
                     const float duration_ms = (float)base_ms * frequency_multiplier * calmness_multiplier;
-                    horizon_ns = f32_as_u64(duration_ms) * 1000000ull;            // from_millis(x as u64)
+                    horizon_ms = f32_as_u64(duration_ms);                         // from_millis(x as u64)
                 }
-                y = ema_step(y, ema_alpha(ft, horizon_ns), xv);
+                if (horizon_ms != ema_ms[k]) {
+                    ema_ms[k] = horizon_ms;
+                    ema_a[k] = ema_alpha(ft, horizon_ms * 1000000ull);
+                }
+                y = ema_step(y, ema_a[k], xv);
             }
             sm[b] = y;
         }
+        if (!ema_cached)   // more bins than the cache covers: the rest without it
+            for (int b = tid + kBinsPerThread * kThreads; b < n; b += kThreads) {
+                const float xv = x[b];
+                xraw[b] = xv;
+                float y = xv;
+                if (P.has_horizon) {
+                    uint64_t horizon_ms = 0;
+                    if (base_ms > 0) {
+                        const float octave_fraction = (float)b / bpo_f / (float)P.octaves;
+                        const float frequency_multiplier = 1.5f - 0.5f * octave_fraction;
+                        horizon_ms = f32_as_u64((float)base_ms * frequency_multiplier * calmness_multiplier);
+                    }
+                    y = ema_step(sm[b], ema_alpha(ft, horizon_ms * 1000000ull), xv);
+                }
+                sm[b] = y;
+            }
         __syncthreads();
+        A_T(a1);
+        A_ACC(0, a0, a1);
 
         // ---- peaks: bass config up to highest_bassnote, general config above (analysis.rs:332-349) --
-        find_peaks_block(sm, n, prm.bassline_peak_config.min_prominence, prm.bassline_peak_config.min_height, distance,
-                         min_bin, st_bass);
-        find_peaks_block(sm, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_gen);
-        // unsmoothed peaks for the calmness update (calmness.rs:39)
-        find_peaks_block(xraw, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_raw);
+        // three searches side by side, a third of the CTA's warps each: the bass configuration, the general
+        // configuration, and the unsmoothed spectrum for the calmness update (calmness.rs:39)
+        {
+            constexpr int kGroup = kThreads / 3;
+            static_assert(kThreads % 96 == 0, "three search groups of whole warps");
+            const int group = tid / kGroup, gtid = tid - group * kGroup;
+            if (group == 0)
+                find_peaks_group(sm, n, prm.bassline_peak_config.min_prominence, prm.bassline_peak_config.min_height, distance,
+                                 min_bin, st_bass, gtid, kGroup, 1, s_warp_min);
+            else if (group == 1)
+                find_peaks_group(sm, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_gen,
+                                 gtid, kGroup, 2, s_warp_min + kGroup / 32);
+            else
+                find_peaks_group(xraw, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_raw,
+                                 gtid, kGroup, 3, s_warp_min + 2 * (kGroup / 32));
+        }
+        __syncthreads();
 
+        A_T(a2);
+        A_ACC(1, a1, a2);
         // ordered compaction of the peak set
         {
             int cnt = 0;
@@ -270,16 +363,15 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
         }
         __syncthreads();
         const int n_peaks = s_npeaks, n_stored = min(n_peaks, kMaxPeaksSmem);
+        A_T(a3);
+        A_ACC(2, a2, a3);
 
         // ---- enhance_peaks_continuous + promote_bass_peaks_with_harmonics (per peak) -----------------
         for (int i = tid; i < n_stored; i += kThreads) {
             const int p = pk_idx[i];
             float center = (float)p, size = sm[p];
             if (p >= 1 && p <= n - 2) {                                           // peak_detection.rs:71-77
-                const float f_prev = P.min_freq * cr_powf(2.0f, (float)(p - 1) / bpo_f);
-                const float f_curr = P.min_freq * cr_powf(2.0f, (float)p / bpo_f);
-                const float f_next = P.min_freq * cr_powf(2.0f, (float)(p + 1) / bpo_f);
-                const float l0 = cr_logf(f_prev), l1 = cr_logf(f_curr), l2 = cr_logf(f_next);
+                const float l0 = logf_bin[p - 1], l1 = logf_bin[p], l2 = logf_bin[p + 1];
                 const float a0 = sm[p - 1], a1 = sm[p], a2 = sm[p + 1];
                 const float denom = (l0 - l1) * (l0 - l2) * (l1 - l2);
                 if (!(fabsf(denom) < 1.1920929e-7f)) {
@@ -328,9 +420,18 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
                 }
             }
             pk_cont[i] = make_float2(center, size);
-            pk_power[i] = cr_powf(10.0f, size / 10.0f);                              // pitch_analysis.rs:58
+            const float power = cr_powf(10.0f, size / 10.0f);                        // pitch_analysis.rs:58
+            pk_power[i] = power;
+            // the per-peak factors of the two sequential passes below (pitch_analysis.rs:24-41, :54-74), computed here in parallel
+            const float cs = center * 12.0f / bpo_f;
+            const float deviation = cs - roundf(cs);
+            pk_dev[i] = deviation;
+            pk_inacc[i] = fabsf(deviation) * power;
+            pk_bin[i] = (int)f32_as_u64(roundf(center));
         }
 
+        A_T(a4);
+        A_ACC(3, a3, a4);
         // ---- peak filter, afterglow, per-bin calmness (afterglow.rs:10-36, calmness.rs:52-85) ---------
         for (int b = tid; b < n; b += kThreads) {
             const float s = sm[b];
@@ -360,34 +461,62 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
             pdev[b] = 0.0f;
         }
         __syncthreads();
+        A_T(a5);
+        A_ACC(4, a4, a5);
 
         // ---- the reference's sequential f32 sums, in its order (calmness.rs:49-90, pitch_analysis.rs:54-74)
+        // Four single threads on four warps: a lone warp issues an instruction every other cycle at best, so the two
+        // 588-term sums of calmness.rs:49-90 (13 cycles per bin when one thread carried both chains, their loads and the
+        // loop) go to a thread each, with nothing but a 16-byte load per four dependent adds in the loop.
+        auto seq_sum = [&](const float *terms) {
+            float acc = 0.0f;
+            int b = 0;
+            if ((n & 3) == 0) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(terms);
+                const int n4 = n >> 2;
+                float4 cur = p4[0];
+                for (int q = 0; q < n4; ++q) {
+                    const float4 nxt = p4[min(q + 1, n4 - 1)];
+                    acc += cur.x;
+                    acc += cur.y;
+                    acc += cur.z;
+                    acc += cur.w;
+                    cur = nxt;
+                }
+                b = n;
+            }
+            for (; b < n; ++b) acc += terms[b];
+            return acc;
+        };
         if (tid == 0) {
-            float wc = 0.0f, ws = 0.0f;
-            for (int b = 0; b < n; ++b) { wc += termc[b]; ws += termw[b]; }
-            if (ws > 0.0f) s_scene = ema_step(s_scene, alpha_scene, wc / ws);
+            s_wc = seq_sum(termc);
+            A_T(a5b);
+            A_ACC(12, a5, a5b);
+        } else if (tid == 96) {
+            s_ws = seq_sum(termw);
         } else if (tid == 32) {
             float inaccuracy_sum = 0.0f, power_sum = 0.0f;
             for (int i = 0; i < n_stored; ++i) {
                 power_sum += pk_power[i];
-                const float cs = pk_cont[i].x * 12.0f / bpo_f;
-                inaccuracy_sum += fabsf(cs - roundf(cs)) * pk_power[i];
+                inaccuracy_sum += pk_inacc[i];
             }
             const float avg = power_sum > 0.0f ? inaccuracy_sum / power_sum : 0.0f;
             s_tuning = ema_step(s_tuning, alpha_tuning, 100.0f * avg);
         } else if (tid == 64) {
-            for (int i = 0; i < n_stored; ++i) {                                  // pitch_analysis.rs:24-41
-                const float cs = pk_cont[i].x * 12.0f / bpo_f;
-                const float deviation = cs - roundf(cs);
-                const int bin = (int)f32_as_u64(roundf(pk_cont[i].x));
+            for (int i = 0; i < n_stored; ++i) {                                  // pitch_analysis.rs:24-41, in peak order
+                const float deviation = pk_dev[i];
+                const int bin = pk_bin[i];
                 if (bin < n) { pacc[bin] = fmaxf(1.0f - 2.0f * fabsf(deviation), 0.0f); pdev[bin] = deviation; }
             }
         }
         __syncthreads();
+        A_T(a6);
+        A_ACC(5, a5, a6);
 
         // ---- per-frame outputs ------------------------------------------------------------------------
         const pvqt_analysis_outputs &O = P.out;
         if (tid == 0) {
+            if (s_ws > 0.0f) s_scene = ema_step(s_scene, alpha_scene, s_wc / s_ws);    // calmness.rs:88-91
             if (O.peak_count) O.peak_count[fo] = (uint32_t)n_peaks;
             if (O.smoothed_scene_calmness) O.smoothed_scene_calmness[fo] = s_scene;
             if (O.smoothed_tuning_grid_inaccuracy) O.smoothed_tuning_grid_inaccuracy[fo] = s_tuning;
@@ -407,6 +536,9 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
             if (O.pitch_deviation) O.pitch_deviation[o] = pdev[b];
         }
         __syncthreads();
+        A_T(a7);
+        A_ACC(6, a6, a7);
+        A_ACC(7, a0, a7);
     }
 
     for (int b = tid; b < n; b += kThreads) {
@@ -420,7 +552,7 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
 
 size_t analysis_smem_bytes(int nb)
 {
-    return sizeof(float) * 9 * (size_t)nb + sizeof(float2) * kMaxPeaksSmem + sizeof(float) * kMaxPeaksSmem +
+    return sizeof(float) * 10 * (size_t)nb + sizeof(float2) * kMaxPeaksSmem + sizeof(float) * 4 * kMaxPeaksSmem +
            sizeof(int) * kMaxPeaksSmem + sizeof(int) * (kThreads + 2) + 3 * (size_t)nb + 16;
 }
 
@@ -701,3 +833,16 @@ int pvqt_analysis_preprocess_batch(pvqt_analysis *a, const float *db, size_t n_b
 }
 
 }  // extern "C"
+
+#ifdef PVQT_ANALYSIS_STATS
+extern "C" int pvqt_debug_analysis_stats(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_analysis_stats, sizeof(g_analysis_stats)) != cudaSuccess) return 7;
+    if (reset) {
+        static unsigned long long zeros[16] = {};
+        cudaMemcpyToSymbol(g_analysis_stats, zeros, sizeof(zeros));
+    }
+    return 0;
+}
+#endif
