@@ -107,8 +107,6 @@ __device__ __forceinline__ bool group_sync_or(int id, int count, bool pred)
     return r != 0;
 }
 
-__device__ __forceinline__ void st_out(unsigned char *st, int b, unsigned char v) { st[b] = v; }
-
 // st[b] = 1 for every peak of x[0..n), else 0.  Called by the gsz threads (whole warps, gtid = 0..gsz-1) of one search
 // group, which synchronise on named barrier `bar`: the three searches of a frame run side by side on three groups of
 // warps -- each search is a chain of short, latency-bound phases, so a third of the CTA finishes one nearly as fast as
@@ -116,12 +114,30 @@ __device__ __forceinline__ void st_out(unsigned char *st, int b, unsigned char v
 __device__ void find_peaks_group(const float *x, int n, float min_prominence, float min_height, int distance,
                                  int min_bin, unsigned char *st, int gtid, int gsz, int bar, float *warp_min)
 {
+    // A thread owns bins gtid, gtid + gsz, ... (at most 32: n <= 4096, gsz >= 128) and keeps their state in two
+    // register bit masks besides st[], which only the neighbours read.
     A_T(p0);
-    // (also the minimum of x: a peak lower than min_prominence above it cannot pass, whatever its surroundings)
+    // strict local maxima, plateaus at their middle, then min_height (peak_detection.rs / find_peaks: the scan marks the
+    // middle (start + end) / 2 of a plateau whose two neighbours are lower; here every bin asks whether it is that
+    // middle, so a thread writes its own bins only and no clearing pass is needed).  Also the minimum of x: a peak lower
+    // than min_prominence above it cannot pass, whatever its surroundings.
+    unsigned und = 0;
     float lo_x = CUDART_INF_F;
-    for (int b = gtid; b < n; b += gsz) {
-        st[b] = kNone;
-        lo_x = fminf(lo_x, x[b]);
+    {
+        int k = 0;
+        for (int c = gtid; c < n; c += gsz, ++k) {
+            const float v = x[c];
+            lo_x = fminf(lo_x, v);
+            bool peak = false;
+            if (c >= 1 && c <= n - 2 && v >= min_height) {
+                int l = c, r = c;
+                while (l >= 1 && x[l - 1] == v) --l;
+                while (r <= n - 2 && x[r + 1] == v) ++r;
+                peak = l >= 1 && r <= n - 2 && x[l - 1] < v && x[r + 1] < v && ((l + r) >> 1) == c;
+            }
+            st[c] = peak ? kUndecided : kNone;
+            und |= (peak ? 1u : 0u) << k;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
@@ -129,47 +145,38 @@ __device__ void find_peaks_group(const float *x, int n, float min_prominence, fl
     group_sync(bar, gsz);
     float x_min = warp_min[0];
     for (int w = 1; w < (gsz >> 5); ++w) x_min = fminf(x_min, warp_min[w]);
-    // strict local maxima, plateaus at their middle, then min_height
-    for (int b = gtid + 1; b < n - 1; b += gsz) {
-        if (x[b - 1] < x[b]) {
-            int ahead = b + 1;
-            while (ahead < n - 1 && x[ahead] == x[b]) ++ahead;
-            if (x[ahead] < x[b] && x[b] >= min_height) st[(b + ahead - 1) >> 1] = kUndecided;
-        }
-    }
-    group_sync(bar, gsz);
     A_T(p1);
     A_ACC(8, p0, p1);
     // min_distance: taller peaks win (greedy by height == repeated "local champion" rounds)
+    unsigned kept = 0;
     if (distance > 1) {
         bool pending;
         do {
-            for (int b = gtid; b < n; b += gsz) {
-                if (st[b] != kUndecided) continue;
+            for (unsigned m = und; m; m &= m - 1) {
+                const int k = __ffs(m) - 1, b = gtid + k * gsz;
                 bool has_kept = false, top = true;
                 const int lo = max(b - distance + 1, 0), hi = min(b + distance - 1, n - 1);
+                const float xb = x[b];
                 for (int j = lo; j <= hi; ++j) {
                     if (j == b) continue;
                     const unsigned char s = st[j];
                     if (s == kKept) has_kept = true;
-                    else if (s == kUndecided && (x[j] > x[b] || (x[j] == x[b] && j > b))) top = false;
+                    else if (s == kUndecided) { const float xj = x[j]; if (xj > xb || (xj == xb && j > b)) top = false; }
                 }
-                if (!has_kept && top) st[b] = kKept;
+                if (!has_kept && top) { st[b] = kKept; kept |= 1u << k; und &= ~(1u << k); }
             }
             group_sync(bar, gsz);
-            pending = false;
-            for (int b = gtid; b < n; b += gsz) {
-                if (st[b] != kUndecided) continue;
+            for (unsigned m = und; m; m &= m - 1) {
+                const int k = __ffs(m) - 1, b = gtid + k * gsz;
                 bool has_kept = false;
                 const int lo = max(b - distance + 1, 0), hi = min(b + distance - 1, n - 1);
                 for (int j = lo; j <= hi; ++j) has_kept |= (j != b && st[j] == kKept);
-                if (has_kept) st[b] = kRemoved;
-                else pending = true;
+                if (has_kept) { st[b] = kRemoved; und &= ~(1u << k); }
             }
-            pending = group_sync_or(bar, gsz, pending);
+            pending = group_sync_or(bar, gsz, und != 0);
         } while (pending);
     } else {
-        for (int b = gtid; b < n; b += gsz) if (st[b] == kUndecided) st[b] = kKept;
+        kept = und;
         group_sync(bar, gsz);
     }
     A_T(p2);
@@ -181,8 +188,9 @@ __device__ void find_peaks_group(const float *x, int n, float min_prominence, fl
     // and the walk of a side ends at the first bin that decides it -- a few bins for a narrow spectral peak, however
     // tall (walking the whole stretch of the tallest peaks, 32 bins at a time by a warp, cost 3.6-8.5 k cycles per
     // search).  One thread per kept bin, its own two short walks.
-    for (int b = gtid; b < n; b += gsz) {
-        if (st[b] != kKept) { st_out(st, b, 0); continue; }
+    unsigned pass = 0;
+    for (unsigned m = kept; m; m &= m - 1) {
+        const int k = __ffs(m) - 1, b = gtid + k * gsz;
         const float h = x[b];
         // every bin is >= x_min and f32 subtraction is monotonic: h - x[i] <= h - x_min < P on both sides
         bool ok = b >= min_bin && h - x_min >= min_prominence;
@@ -197,7 +205,11 @@ __device__ void find_peaks_group(const float *x, int n, float min_prominence, fl
             // (the peak itself belongs to the stretch: h - h >= P only for P <= 0)
             ok = deep || (h - h >= min_prominence);
         }
-        st_out(st, b, ok ? 1 : 0);
+        pass |= (ok ? 1u : 0u) << k;
+    }
+    {
+        int k = 0;
+        for (int b = gtid; b < n; b += gsz, ++k) st[b] = (pass >> k) & 1u;
     }
     A_T(p3);
     A_ACC(10, p2, p3);
