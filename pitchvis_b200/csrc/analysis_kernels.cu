@@ -89,6 +89,14 @@ __device__ __forceinline__ float ema_alpha(float timestep_s, uint64_t horizon_ns
 {
     return 1.0f - cr_expf(-2.0f * timestep_s / dur_as_secs_f32(horizon_ns));
 }
+// the same for a horizon of whole milliseconds (Duration::from_millis(ms).as_secs_f32()): ms / 1000 s + (ms % 1000) * 1e6 ns,
+// without the 64-bit division by 1e9 (the EMA of the spectrum re-evaluates alpha whenever a bin's horizon changes)
+__device__ __forceinline__ float ema_alpha_ms(float timestep_s, uint64_t horizon_ms)
+{
+    if (horizon_ms > 0xffffffffull) return ema_alpha(timestep_s, horizon_ms * 1000000ull);
+    const uint32_t ms = (uint32_t)horizon_ms, secs = ms / 1000u, sub_ns = (ms - secs * 1000u) * 1000000u;
+    return 1.0f - cr_expf(-2.0f * timestep_s / ((float)secs + (float)sub_ns / 1000000000.0f));
+}
 __device__ __forceinline__ float ema_step(float y, float alpha, float x) { return y + alpha * (x - y); }  // util.rs:124
 
 // ---- cooperative peak search (find_peaks wrapper, peak_detection.rs:26-51) -------------------------
@@ -123,20 +131,36 @@ __device__ void find_peaks_group(const float *x, int n, float min_prominence, fl
     // than min_prominence above it cannot pass, whatever its surroundings.
     unsigned und = 0;
     float lo_x = CUDART_INF_F;
-    {
-        int k = 0;
-        for (int c = gtid; c < n; c += gsz, ++k) {
-            const float v = x[c];
-            lo_x = fminf(lo_x, v);
-            bool peak = false;
-            if (c >= 1 && c <= n - 2 && v >= min_height) {
-                int l = c, r = c;
-                while (l >= 1 && x[l - 1] == v) --l;
-                while (r <= n - 2 && x[r + 1] == v) ++r;
-                peak = l >= 1 && r <= n - 2 && x[l - 1] < v && x[r + 1] < v && ((l + r) >> 1) == c;
+    for (int k0 = 0; gtid + k0 * gsz < n; k0 += 8) {       // eight of the thread's bins at a time: their loads issue together
+        float vm[8], v0[8], vp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = gtid + (k0 + u) * gsz;
+            const bool in = c < n;
+            v0[u] = in ? x[c] : 0.0f;
+            vm[u] = in && c >= 1 ? x[c - 1] : 0.0f;
+            vp[u] = in && c <= n - 2 ? x[c + 1] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = gtid + (k0 + u) * gsz;
+            if (c < n) {
+                const float v = v0[u];
+                lo_x = fminf(lo_x, v);
+                bool peak = false;
+                if (c >= 1 && c <= n - 2 && v >= min_height) {
+                    if (vm[u] < v && vp[u] < v) {
+                        peak = true;                            // the usual case: no plateau
+                    } else if (vm[u] == v || vp[u] == v) {
+                        int l = c, r = c;
+                        while (l >= 1 && x[l - 1] == v) --l;
+                        while (r <= n - 2 && x[r + 1] == v) ++r;
+                        peak = l >= 1 && r <= n - 2 && x[l - 1] < v && x[r + 1] < v && ((l + r) >> 1) == c;
+                    }
+                }
+                st[c] = peak ? kUndecided : kNone;
+                und |= (peak ? 1u : 0u) << (k0 + u);
             }
-            st[c] = peak ? kUndecided : kNone;
-            und |= (peak ? 1u : 0u) << k;
         }
     }
 #pragma unroll
@@ -254,6 +278,7 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
     const float alpha_tuning = ema_alpha(ft, prm.tuning_inaccuracy_smoothing_duration_ns);
     const uint64_t base_ms = prm.vqt_smoothing_duration_base_ns / 1000000ull;   // as_millis()
     const float bpo_f = (float)P.bpo;
+    const float log2_min_freq = cr_log2f(P.min_freq);
     const int distance = (int)f32_as_u64(roundf(bpo_f * 0.4f / 12.0f));         // peak_detection.rs:37
     const int min_bin = (P.bpo / 12 + 1) / 2;                                   // peak_detection.rs:45
     const int radius = P.bpo / 12 / 3;                                          // calmness.rs:36
@@ -269,6 +294,13 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) { ema_ms[k] = ~0ull; ema_a[k] = 0.0f; }
     const bool ema_cached = n <= kBinsPerThread * kThreads;
+    float base_fm[kBinsPerThread];   // base horizon x the bin's frequency multiplier (analysis.rs:309-318), frame-independent
+#pragma unroll
+    for (int k = 0; k < kBinsPerThread; ++k) {
+        const float octave_fraction = (float)(tid + k * kThreads) / bpo_f / (float)P.octaves;
+        const float frequency_multiplier = 1.5f - 0.5f * octave_fraction;
+        base_fm[k] = (float)base_ms * frequency_multiplier;
+    }
     float x_next[kBinsPerThread];
 #pragma unroll
     for (int k = 0; k < kBinsPerThread; ++k) {
@@ -295,15 +327,10 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
                 y = xv;                                                           // util.rs:117-120
             } else {
                 uint64_t horizon_ms = 0;                                          // base 0 ms: horizon stays 0 ms
-                if (base_ms > 0) {
-                    const float octave_fraction = (float)b / bpo_f / (float)P.octaves;
-                    const float frequency_multiplier = 1.5f - 0.5f * octave_fraction;
-                    const float duration_ms = (float)base_ms * frequency_multiplier * calmness_multiplier;
-                    horizon_ms = f32_as_u64(duration_ms);                         // from_millis(x as u64)
-                }
+                if (base_ms > 0) horizon_ms = f32_as_u64(base_fm[k] * calmness_multiplier);   // from_millis(x as u64)
                 if (horizon_ms != ema_ms[k]) {
                     ema_ms[k] = horizon_ms;
-                    ema_a[k] = ema_alpha(ft, horizon_ms * 1000000ull);
+                    ema_a[k] = ema_alpha_ms(ft, horizon_ms);
                 }
                 y = ema_step(y, ema_a[k], xv);
             }
@@ -415,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
                 for (int h = 2; h <= 5; ++h) {
                     const float harmonic_freq = fundamental_freq * (float)h;
                     if (!(harmonic_freq >= P.min_freq)) continue;
-                    const float harmonic_bin = (cr_log2f(harmonic_freq) - cr_log2f(P.min_freq)) * bpo_f;
+                    const float harmonic_bin = (cr_log2f(harmonic_freq) - log2_min_freq) * bpo_f;
                     if (harmonic_bin >= 0.0f && harmonic_bin < (float)n) {
                         const int lo = (int)f32_as_u64(floorf(harmonic_bin));
                         const int hi2 = min((int)f32_as_u64(ceilf(harmonic_bin)), n - 1);
