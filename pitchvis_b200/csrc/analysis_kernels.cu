@@ -377,7 +377,39 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
 
         A_T(a2);
         A_ACC(1, a1, a2);
-        // ordered compaction of the peak set
+        // (this per-bin pass needs the unsmoothed peaks only; it runs before the compaction so that the two long
+        // sequential sums over its terms can run beside the per-peak work below)
+        // ---- peak filter, afterglow, per-bin calmness (afterglow.rs:10-36, calmness.rs:52-85) ---------
+        for (int b = tid; b < n; b += kThreads) {
+            const float s = sm[b];
+            float g = aglow[b];
+            g *= 0.85f - 0.15f * ((float)b / (float)n);
+            if (g < s) g = s;
+            aglow[b] = g;
+            bool has_peak = false;                                                // [p - r, p + r) around unsmoothed peaks
+            for (int p = max(b - radius + 1, 0); p <= min(b + radius, n - 1); ++p) has_peak |= st_raw[p] != 0;
+            float c = calm[b], tc = 0.0f, tw = 0.0f;
+            if (has_peak) {
+                c = ema_step(c, alpha_calm, 1.0f);
+                released[b] = c;
+                const float amplitude_power = cr_powf(10.0f, s / 10.0f);
+                tc = c * amplitude_power;
+                tw = amplitude_power;
+            } else {
+                c = ema_step(c, alpha_calm, 0.0f);
+                const float rc = ema_step(released[b], alpha_calm, 0.0f);
+                released[b] = rc;
+                if (rc > 0.01f) { tw = rc * 0.3f; tc = rc * tw; }
+            }
+            calm[b] = c;
+            termc[b] = tc;
+            termw[b] = tw;
+            pacc[b] = 0.0f;
+            pdev[b] = 0.0f;
+        }
+        A_T(a2b);
+        A_ACC(4, a2, a2b);
+        // ordered compaction of the peak set (its barriers also publish the terms above)
         {
             int cnt = 0;
             const int b0 = tid * chunk, b1 = min(b0 + chunk, n);
@@ -403,7 +435,36 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
         __syncthreads();
         const int n_peaks = s_npeaks, n_stored = min(n_peaks, kMaxPeaksSmem);
         A_T(a3);
-        A_ACC(2, a2, a3);
+        A_ACC(2, a2b, a3);
+
+        // ---- the reference's sequential f32 sums, in its order (calmness.rs:49-90, pitch_analysis.rs:54-74)
+        // Four single threads on four warps: a lone warp issues an instruction every other cycle at best, so the two
+        // 588-term sums of calmness.rs:49-90 (13 cycles per bin when one thread carried both chains, their loads and the
+        // loop) go to a thread each, with nothing but a 16-byte load per four dependent adds in the loop.
+        auto seq_sum = [&](const float *terms) {
+            float acc = 0.0f;
+            int b = 0;
+            if ((n & 3) == 0) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(terms);
+                const int n4 = n >> 2;
+                float4 cur = p4[0];
+                for (int q = 0; q < n4; ++q) {
+                    const float4 nxt = p4[min(q + 1, n4 - 1)];
+                    acc += cur.x;
+                    acc += cur.y;
+                    acc += cur.z;
+                    acc += cur.w;
+                    cur = nxt;
+                }
+                b = n;
+            }
+            for (; b < n; ++b) acc += terms[b];
+            return acc;
+        };
+        // threads 256 and 288 own no peak (at most 256 are stored): their warps carry the two sums beside the per-peak work
+        static_assert(kThreads > 288 && kMaxPeaksSmem <= 256, "threads 256 and 288 must exist and own no peak");
+        if (tid == 256) s_wc = seq_sum(termc);
+        else if (tid == 288) s_ws = seq_sum(termw);
 
         // ---- enhance_peaks_continuous + promote_bass_peaks_with_harmonics (per peak) -----------------
         for (int i = tid; i < n_stored; i += kThreads) {
@@ -469,71 +530,11 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
             pk_bin[i] = (int)f32_as_u64(roundf(center));
         }
 
+        __syncthreads();
         A_T(a4);
         A_ACC(3, a3, a4);
-        // ---- peak filter, afterglow, per-bin calmness (afterglow.rs:10-36, calmness.rs:52-85) ---------
-        for (int b = tid; b < n; b += kThreads) {
-            const float s = sm[b];
-            float g = aglow[b];
-            g *= 0.85f - 0.15f * ((float)b / (float)n);
-            if (g < s) g = s;
-            aglow[b] = g;
-            bool has_peak = false;                                                // [p - r, p + r) around unsmoothed peaks
-            for (int p = max(b - radius + 1, 0); p <= min(b + radius, n - 1); ++p) has_peak |= st_raw[p] != 0;
-            float c = calm[b], tc = 0.0f, tw = 0.0f;
-            if (has_peak) {
-                c = ema_step(c, alpha_calm, 1.0f);
-                released[b] = c;
-                const float amplitude_power = cr_powf(10.0f, s / 10.0f);
-                tc = c * amplitude_power;
-                tw = amplitude_power;
-            } else {
-                c = ema_step(c, alpha_calm, 0.0f);
-                const float rc = ema_step(released[b], alpha_calm, 0.0f);
-                released[b] = rc;
-                if (rc > 0.01f) { tw = rc * 0.3f; tc = rc * tw; }
-            }
-            calm[b] = c;
-            termc[b] = tc;
-            termw[b] = tw;
-            pacc[b] = 0.0f;
-            pdev[b] = 0.0f;
-        }
-        __syncthreads();
-        A_T(a5);
-        A_ACC(4, a4, a5);
 
-        // ---- the reference's sequential f32 sums, in its order (calmness.rs:49-90, pitch_analysis.rs:54-74)
-        // Four single threads on four warps: a lone warp issues an instruction every other cycle at best, so the two
-        // 588-term sums of calmness.rs:49-90 (13 cycles per bin when one thread carried both chains, their loads and the
-        // loop) go to a thread each, with nothing but a 16-byte load per four dependent adds in the loop.
-        auto seq_sum = [&](const float *terms) {
-            float acc = 0.0f;
-            int b = 0;
-            if ((n & 3) == 0) {
-                const float4 *p4 = reinterpret_cast<const float4 *>(terms);
-                const int n4 = n >> 2;
-                float4 cur = p4[0];
-                for (int q = 0; q < n4; ++q) {
-                    const float4 nxt = p4[min(q + 1, n4 - 1)];
-                    acc += cur.x;
-                    acc += cur.y;
-                    acc += cur.z;
-                    acc += cur.w;
-                    cur = nxt;
-                }
-                b = n;
-            }
-            for (; b < n; ++b) acc += terms[b];
-            return acc;
-        };
-        if (tid == 0) {
-            s_wc = seq_sum(termc);
-            A_T(a5b);
-            A_ACC(12, a5, a5b);
-        } else if (tid == 96) {
-            s_ws = seq_sum(termw);
-        } else if (tid == 32) {
+        if (tid == 32) {
             float inaccuracy_sum = 0.0f, power_sum = 0.0f;
             for (int i = 0; i < n_stored; ++i) {
                 power_sum += pk_power[i];
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constan
         }
         __syncthreads();
         A_T(a6);
-        A_ACC(5, a5, a6);
+        A_ACC(5, a4, a6);
 
         // ---- per-frame outputs ------------------------------------------------------------------------
         const pvqt_analysis_outputs &O = P.out;

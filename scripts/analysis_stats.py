@@ -19,8 +19,8 @@ t0 = time.perf_counter()
 res = st.preprocess_batch(db, 16_689_342)
 dt = time.perf_counter() - t0
 lib.pvqt_debug_analysis_stats(buf.ctypes.data, 1)
-names = ["EMA of the spectrum", "three peak searches", "compaction", "enhance + bass promotion (per peak)", "afterglow / calmness (per bin)",
-         "sequential sums", "outputs", "frame total", "  peak search: maxima", "  peak search: min distance", "  peak search: prominence (thread 0's warp)", "", "  sequential sums: thread 0's own loop"]
+names = ["EMA of the spectrum", "three peak searches", "compaction", "enhance + bass promotion (per peak) | the two 588-term sums", "afterglow / calmness (per bin)",
+         "sequential passes over the peaks", "outputs", "frame total", "  peak search: maxima", "  peak search: min distance", "  peak search: prominence (thread 0's warp)"]
 print(f"{n} frames, {dt * 1e3:.1f} ms per call = {dt / n * 1e6:.1f} us per frame (host buffers in and out); cycles per frame, thread 0:")
 for i, nm in enumerate(names):
     if not nm: continue
