@@ -119,7 +119,7 @@ __device__ __forceinline__ bool group_sync_or(int id, int count, bool pred)
 // group, which synchronise on named barrier `bar`: the three searches of a frame run side by side on three groups of
 // warps -- each search is a chain of short, latency-bound phases, so a third of the CTA finishes one nearly as fast as
 // the whole CTA did (10 k cycles each, one after the other, before: profiles/r02_f_analysis_phase_cycles.txt).
-__device__ void find_peaks_group(const float *x, int n, float min_prominence, float min_height, int distance,
+__device__ __forceinline__ void find_peaks_group(const float *x, int n, float min_prominence, float min_height, int distance,
                                  int min_bin, unsigned char *st, int gtid, int gsz, int bar, float *warp_min)
 {
     // A thread owns bins gtid, gtid + gsz, ... (at most 32: n <= 4096, gsz >= 128) and keeps their state in two
@@ -239,7 +239,11 @@ __device__ void find_peaks_group(const float *x, int n, float min_prominence, fl
     A_ACC(10, p2, p3);
 }
 
-__global__ void __launch_bounds__(kThreads) analysis_kernel(const __grid_constant__ AnalysisKernelParams P)
+// Two register budgets: MIN_CTAS = 1 (167 registers, nothing spilled) for a few streams, where a frame's latency is the
+// job's time; MIN_CTAS = 2 (80 registers, ~400 bytes spilled, two CTAs per SM) when there are more streams than SMs and the
+// second resident CTA is worth more than the spills cost (one 60 s stream 38 against 42 ms; 1024 streams 5.1 against 5.4 M frames/s).
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(kThreads, MIN_CTAS) analysis_kernel(const __grid_constant__ AnalysisKernelParams P)
 {
     extern __shared__ __align__(16) unsigned char a_smem[];
     const int n = P.nb, tid = threadIdx.x, stream = blockIdx.x;
@@ -693,7 +697,9 @@ int pvqt_analysis_create(const pvqt_range *range, const pvqt_analysis_params *pa
     }
     ACUDA(cudaMalloc(&a->st_scalar, n_streams * 2 * sizeof(float)));
     ACUDA(cudaMemset(a->st_scalar, 0, n_streams * 2 * sizeof(float)));
-    ACUDA(cudaFuncSetAttribute(analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ACUDA(cudaFuncSetAttribute(analysis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)analysis_smem_bytes((int)nb)));
+    ACUDA(cudaFuncSetAttribute(analysis_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)analysis_smem_bytes((int)nb)));
     *out = a.release();
     return PVQT_OK;
@@ -762,7 +768,10 @@ int pvqt_detail::analysis_run_device(pvqt_analysis *a, const float *d_db, size_t
                 out_member(P.out, i) = static_cast<char *>(out_member(P.out, i)) +
                                        out_frame_offset * out_bytes_per_frame(i, a->nb, d_out->max_peaks);
     }
-    analysis_kernel<<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device) != cudaSuccess) sms = 148;
+    if ((size_t)n_streams > (size_t)sms) analysis_kernel<2><<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
+    else analysis_kernel<1><<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
     ACUDA(cudaGetLastError());
     return PVQT_OK;
 }
