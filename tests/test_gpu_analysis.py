@@ -252,3 +252,28 @@ def test_all_117_close_tone_cases_through_the_gpu(vqt):
     res = a.preprocess_batch(db[:, None, :], 1100 * 1_000_000, vectors=False)
     assert res["peak_count"][:, 0].tolist() == [2] * len(cases)
     a.close()
+
+
+@pytest.mark.parametrize("range_", [(55.0, 7, 84), (55.0, 8, 168), (55.0, 2, 24)])
+def test_plateaus_ties_and_bin_counts(built_lib, range_):
+    # Synthetic dB frames quantised to 0.5 dB: plateaus of equal maxima, equal-height neighbours inside the distance
+    # window, long flat floors (the prominence walks run far) -- at 588, 1344 (more than 8 bins per search thread) and
+    # 48 bins.  Peak sets must equal the oracle's in every frame.
+    nb = range_[1] * range_[2]
+    rng = np.random.default_rng(7)
+    T = 48
+    db = np.zeros((T, nb), np.float32)
+    x = np.arange(nb)
+    for t in range(T):
+        frame = np.zeros(nb)
+        for _ in range(int(rng.integers(5, 40))):
+            c, w, h = rng.uniform(0, nb), rng.uniform(1.0, 12.0), rng.uniform(2.0, 45.0)
+            frame += h * np.exp(-0.5 * ((x - c) / w) ** 2)
+        frame += rng.uniform(0.0, 3.0, nb) * (rng.random(nb) < 0.3)
+        db[t] = np.round(np.minimum(frame, 60.0) * 2.0) / 2.0          # ties and plateaus
+    a = pv.AnalysisState(pv.VqtRange(*range_), n_streams=1)
+    res = a.preprocess_batch(db, FRAME_NS)
+    ref = _oracle_run(db, FRAME_NS, range_=range_)
+    assert sum(len(p) for p in ref["peaks"]) > (50 if nb > 100 else 10)
+    _compare(res, 0, ref, T)
+    a.close()
