@@ -2132,15 +2132,28 @@ int pvqt_calc_streams_analysis(pvqt *v, pvqt_analysis *a, const float *audio, si
     const size_t span = (frames_per_stream - 1) * hop + n_fft, dstride = (span + 3) & ~(size_t)3;
     const size_t group = std::max<size_t>(1, v->staging_budget_samples / dstride);
     size_t total_d2h = 0;
+    const bool timing = std::getenv("PVQT_DEBUG_TIMING") != nullptr;   // diagnostic: drains the stream between the stages
+    auto stamp = [&](const char *what, size_t g0) {
+        if (!timing) return;
+        cudaStreamSynchronize(v->stream);
+        static auto t_prev = std::chrono::steady_clock::now();
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "pvqt_calc_streams_analysis: %-22s group at stream %zu: +%.2f ms\n", what, g0,
+                     std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
+    stamp("start", 0);
     for (size_t g0 = 0; g0 < n_streams; g0 += group) {
         const size_t ng = std::min(group, n_streams - g0);
         rc = run_host(v, audio + g0 * stream_stride, ng, stream_stride, n_samples, hop, frames_per_stream, nullptr, true);
         if (rc) return rc;
+        stamp("H2D + VQT", g0);
         const float *d_db = static_cast<const float *>(v->d_out.ptr);
         rc = pvqt_detail::analysis_run_device(a, d_db, g0, ng, frames_per_stream, frame_time_ns, out ? &dev : nullptr,
                                               g0 * frames_per_stream, v->stream);
         if (rc) return rc;
         v->launches.fetch_add(1);
+        stamp("K-analysis", g0);
         if (out_db) {
             const size_t bytes = ng * frames_per_stream * nb * sizeof(float);
             PVQT_CUDA(cudaMemcpyAsync(out_db + g0 * frames_per_stream * nb, d_db, bytes, cudaMemcpyDeviceToHost, v->stream));
@@ -2152,6 +2165,7 @@ int pvqt_calc_streams_analysis(pvqt *v, pvqt_analysis *a, const float *audio, si
     rc = pvqt_detail::analysis_outputs_download(a, out, &dev, frames, v->stream, &res_bytes);
     if (rc) return rc;
     PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    stamp("download of the results", 0);
     if (d2h_bytes) *d2h_bytes = total_d2h + res_bytes;
     return PVQT_OK;
 }
