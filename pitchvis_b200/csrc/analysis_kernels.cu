@@ -11,6 +11,7 @@
 // the rare last-bit differences of correctly rounded transcendentals (cr_* below).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -38,6 +39,7 @@ int acuda(cudaError_t e, const char *what)
     } while (0)
 
 constexpr int kThreads = 384;   // 12 warps: three search groups of four
+constexpr int kSmallThreads = 128;   // the many-stream form (see the launch)
 constexpr int kMaxPeaksSmem = 256;  // peaks of one frame kept in shared memory (588 bins, distance 3 -> <= 196)
 
 struct AnalysisKernelParams {
@@ -242,9 +244,10 @@ __device__ __forceinline__ void find_peaks_group(const float *x, int n, float mi
 // Two register budgets: MIN_CTAS = 1 (167 registers, nothing spilled) for a few streams, where a frame's latency is the
 // job's time; MIN_CTAS = 2 (80 registers, ~400 bytes spilled, two CTAs per SM) when there are more streams than SMs and the
 // second resident CTA is worth more than the spills cost (one 60 s stream 38 against 42 ms; 1024 streams 5.1 against 5.4 M frames/s).
-template <int MIN_CTAS>
-__global__ void __launch_bounds__(kThreads, MIN_CTAS) analysis_kernel(const __grid_constant__ AnalysisKernelParams P)
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) analysis_kernel(const __grid_constant__ AnalysisKernelParams P)
 {
+    constexpr int kThreads = THREADS;   // (shadows the default CTA size below)
     extern __shared__ __align__(16) unsigned char a_smem[];
     const int n = P.nb, tid = threadIdx.x, stream = blockIdx.x;
     float *xraw = reinterpret_cast<float *>(a_smem);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) analysis_kernel(const __gr
         // ---- peaks: bass config up to highest_bassnote, general config above (analysis.rs:332-349) --
         // three searches side by side, a third of the CTA's warps each: the bass configuration, the general
         // configuration, and the unsmoothed spectrum for the calmness update (calmness.rs:39)
-        {
+        if constexpr (kThreads >= 384) {
             constexpr int kGroup = kThreads / 3;
             static_assert(kThreads % 96 == 0, "three search groups of whole warps");
             const int group = tid / kGroup, gtid = tid - group * kGroup;
@@ -376,6 +379,14 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) analysis_kernel(const __gr
             else
                 find_peaks_group(xraw, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_raw,
                                  gtid, kGroup, 3, s_warp_min + 2 * (kGroup / 32));
+        } else {
+            // the small CTA of the many-stream form: one group, the three searches one after the other
+            find_peaks_group(sm, n, prm.bassline_peak_config.min_prominence, prm.bassline_peak_config.min_height, distance,
+                             min_bin, st_bass, tid, kThreads, 1, s_warp_min);
+            find_peaks_group(sm, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_gen,
+                             tid, kThreads, 1, s_warp_min);
+            find_peaks_group(xraw, n, prm.peak_config.min_prominence, prm.peak_config.min_height, distance, min_bin, st_raw,
+                             tid, kThreads, 1, s_warp_min);
         }
         __syncthreads();
 
@@ -465,10 +476,12 @@ __global__ void __launch_bounds__(kThreads, MIN_CTAS) analysis_kernel(const __gr
             for (; b < n; ++b) acc += terms[b];
             return acc;
         };
-        // threads 256 and 288 own no peak (at most 256 are stored): their warps carry the two sums beside the per-peak work
-        static_assert(kThreads > 288 && kMaxPeaksSmem <= 256, "threads 256 and 288 must exist and own no peak");
-        if (tid == 256) s_wc = seq_sum(termc);
-        else if (tid == 288) s_ws = seq_sum(termw);
+        // two threads on two warps carry the two sums beside the per-peak work: 256 and 288 in the large CTA, which own no
+        // peak (at most 256 are stored); the last two warps' first threads in the small one (they refine their peaks after)
+        constexpr int kSumA = kThreads >= 384 ? 256 : kThreads - 64, kSumB = kThreads >= 384 ? 288 : kThreads - 32;
+        static_assert(kMaxPeaksSmem <= 256 && kSumA >= 64, "see above");
+        if (tid == kSumA) s_wc = seq_sum(termc);
+        else if (tid == kSumB) s_ws = seq_sum(termw);
 
         // ---- enhance_peaks_continuous + promote_bass_peaks_with_harmonics (per peak) -----------------
         for (int i = tid; i < n_stored; i += kThreads) {
@@ -697,10 +710,9 @@ int pvqt_analysis_create(const pvqt_range *range, const pvqt_analysis_params *pa
     }
     ACUDA(cudaMalloc(&a->st_scalar, n_streams * 2 * sizeof(float)));
     ACUDA(cudaMemset(a->st_scalar, 0, n_streams * 2 * sizeof(float)));
-    ACUDA(cudaFuncSetAttribute(analysis_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)analysis_smem_bytes((int)nb)));
-    ACUDA(cudaFuncSetAttribute(analysis_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)analysis_smem_bytes((int)nb)));
+    for (auto k : {(const void *)analysis_kernel<kThreads, 1>, (const void *)analysis_kernel<kThreads, 2>,
+                   (const void *)analysis_kernel<kSmallThreads, 5>})
+        ACUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_smem_bytes((int)nb)));
     *out = a.release();
     return PVQT_OK;
 }
@@ -770,8 +782,15 @@ int pvqt_detail::analysis_run_device(pvqt_analysis *a, const float *d_db, size_t
     }
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, a->device) != cudaSuccess) sms = 148;
-    if ((size_t)n_streams > (size_t)sms) analysis_kernel<2><<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
-    else analysis_kernel<1><<<(unsigned)n_streams, kThreads, analysis_smem_bytes((int)a->nb), st>>>(P);
+    const size_t smem = analysis_smem_bytes((int)a->nb);
+    // up to one stream per SM: the large CTA with all its registers (a frame's latency is the job's time); up to two:
+    // the large CTA twice per SM; beyond: small CTAs, five per SM (1024 streams x 511 frames: 36.7 against 40.7 ms -- with
+    // many streams the SM is no longer waiting but issuing, ~10 us of f64 transcendentals and searches per frame and SM)
+    if (std::getenv("PVQT_ANALYSIS_SMALL_CTA")) analysis_kernel<kSmallThreads, 5><<<(unsigned)n_streams, kSmallThreads, smem, st>>>(P);   // (tests)
+    else if ((size_t)n_streams <= (size_t)sms) analysis_kernel<kThreads, 1><<<(unsigned)n_streams, kThreads, smem, st>>>(P);
+    else if ((size_t)n_streams <= 2 * (size_t)sms || std::getenv("PVQT_ANALYSIS_LARGE_CTA"))
+        analysis_kernel<kThreads, 2><<<(unsigned)n_streams, kThreads, smem, st>>>(P);
+    else analysis_kernel<kSmallThreads, 5><<<(unsigned)n_streams, kSmallThreads, smem, st>>>(P);
     ACUDA(cudaGetLastError());
     return PVQT_OK;
 }

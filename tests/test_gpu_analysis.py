@@ -277,3 +277,20 @@ def test_plateaus_ties_and_bin_counts(built_lib, range_):
     assert sum(len(p) for p in ref["peaks"]) > (50 if nb > 100 else 10)
     _compare(res, 0, ref, T)
     a.close()
+
+
+def test_small_cta_form_gives_the_same_results(vqt, monkeypatch):
+    # more than two streams per SM run in 128-thread CTAs (three searches one after the other): same results, bit for bit
+    audio = synth.polyphonic_chords(6.0, 22050.0, seed=3)
+    db = vqt.calculate_vqt_batch_in_db(audio, HOP)
+    S = 3
+    many = np.stack([np.roll(db, 7 * s, axis=0) for s in range(S)])
+    big = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    ref = big.preprocess_batch(many, FRAME_NS)
+    big.close()
+    monkeypatch.setenv("PVQT_ANALYSIS_SMALL_CTA", "1")
+    small = pv.AnalysisState(pv.VqtRange(), n_streams=S)
+    got = small.preprocess_batch(many, FRAME_NS)
+    small.close()
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), k
