@@ -713,6 +713,29 @@ def bench_pipeline(ctx: Ctx, streams_audio=None):
         "cpu_port": {"seconds": t_vqt + t_ana, "value": T / (t_vqt + t_ana), "vqt_seconds": t_vqt, "analysis_seconds": t_ana,
                      "cores": threads, "kind": "port",
                      "note": "oracle VQT (f32, all host threads) + oracle AnalysisState epilogue (sequential, one thread)"}}
+    # the viewer's loop (vqt_system.rs:40-68 + analysis_system.rs:10-20): one frame of audio per call, 60 times a second
+    n_fft = 32768
+    live = pv.AnalysisState(pv.VqtRange(), device=ctx.local_rank)
+    lat = []
+    for t in range(450):
+        x = np.ascontiguousarray(audio[t * hop:t * hop + n_fft])
+        t0 = time.perf_counter()
+        live.calculate_and_preprocess(v, x, hop, FRAME_NS, frames_per_stream=1, max_peaks=32)
+        lat.append(time.perf_counter() - t0)
+    live.close()
+    lat = np.array(lat[50:]) * 1e6
+    # the CPU port frame by frame on one core: the VQT with its scratch set up once, then the epilogue
+    t0 = time.perf_counter()
+    o.calculate_batch_db(audio[:255 * hop + n_fft], hop, 256, mode=1, n_threads=1)
+    cpu_vqt_us = (time.perf_counter() - t0) / 256 * 1e6
+    rec["frame_by_frame"] = {
+        "workload": "one frame of audio per call through pvqt_calc_batch_analysis (n_frames = 1): host x[n_fft] in, peaks and "
+                    "scalars out, the AnalysisState advancing from call to call",
+        "api": "pinned staging both ways, one captured graph per call: H2D, K-fft, K-spmm-db, K-analysis, one D2H",
+        "p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "min_us": float(lat.min()),
+        "calls": int(lat.size), "includes": "the Python wrapper's result-array allocation per call (~10 us)",
+        "cpu_port": {"us_per_frame": cpu_vqt_us + 1e6 * t_ana / T, "vqt_us": cpu_vqt_us, "analysis_us": 1e6 * t_ana / T,
+                     "cores": 1, "kind": "port"}}
     # many streams: stream-parallel epilogue, one CTA per stream
     if streams_audio is not None and streams_audio.shape[0] >= 64:
         S = min(streams_audio.shape[0], 1024)

@@ -10,6 +10,7 @@
 // truncated to whole milliseconds (analysis.rs:319), so rounding differences are kept to libm's
 // the rare last-bit differences of correctly rounded transcendentals (cr_* below).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -627,6 +628,13 @@ struct pvqt_analysis {
     static constexpr int kOutputs = 11;
     void *mirror[kOutputs] = {};
     size_t mirror_bytes[kOutputs] = {};
+    uint64_t generation = next_generation_base();   // unique per handle (upper bits) and bumped when the parameters or a
+                                                    // mirror change: captured per-frame launches key on it
+    static uint64_t next_generation_base()
+    {
+        static std::atomic<uint64_t> handles{0};
+        return (handles.fetch_add(1) + 1) << 32;
+    }
 };
 
 namespace {
@@ -733,6 +741,7 @@ size_t pvqt_analysis_n_streams(const pvqt_analysis *a) { return a ? a->n_streams
 int pvqt_analysis_update_vqt_smoothing_duration(pvqt_analysis *a, int has_duration, uint64_t duration_ns)
 {
     if (!a) return afail(PVQT_INVALID_ARGUMENT, "null handle");
+    ++a->generation;
     a->params.vqt_smoothing_duration_base_ns = has_duration ? duration_ns : 0;  // analysis.rs:253
     a->has_horizon = has_duration ? 1 : 0;                                       // analysis.rs:257-268
     return PVQT_OK;
@@ -750,6 +759,12 @@ int pvqt_analysis_preprocess_device(pvqt_analysis *a, const float *d_db, size_t 
 }  // extern "C"
 
 int pvqt_detail::analysis_device(const pvqt_analysis *a) { return a ? a->device : -1; }
+uint64_t pvqt_detail::analysis_generation(const pvqt_analysis *a) { return a ? a->generation : 0; }
+void *&pvqt_detail::analysis_output_member(pvqt_analysis_outputs &o, int i) { return out_member(o, i); }
+size_t pvqt_detail::analysis_output_bytes_per_frame(const pvqt_analysis *a, int i, size_t max_peaks)
+{
+    return out_bytes_per_frame(i, a->nb, max_peaks);
+}
 
 int pvqt_detail::analysis_run_device(pvqt_analysis *a, const float *d_db, size_t first_stream, size_t n_streams,
                                      size_t n_frames, uint64_t frame_time_ns, const pvqt_analysis_outputs *d_out,
@@ -812,6 +827,7 @@ int pvqt_detail::analysis_outputs_reserve(pvqt_analysis *a, const pvqt_analysis_
             a->mirror_bytes[i] = 0;
             ACUDA(cudaMalloc(&a->mirror[i], bytes));
             a->mirror_bytes[i] = bytes;
+            ++a->generation;
         }
         // slots past a frame's peak_count stay 0
         if (i == 1 || i == 2) ACUDA(cudaMemsetAsync(a->mirror[i], 0, bytes, stream));

@@ -223,7 +223,23 @@ struct pvqt {
         int calls = 0;
     } instant;
 
+    // pvqt_calc_batch_analysis with one frame per call (what the reference's viewer does 60 times a second): pinned staging
+    // both ways and one captured graph -- H2D, K-fft, K-spmm-db, K-analysis, D2H of the requested results
+    struct FramePipe {
+        float *h_in = nullptr, *d_in = nullptr, *d_db = nullptr;
+        char *h_res = nullptr, *d_res = nullptr;   // pinned / device: the requested result arrays of one frame, back to back
+        size_t h_res_bytes = 0;
+        cudaGraphExec_t exec = nullptr;
+        const void *analysis = nullptr;            // what `exec` was captured for
+        uint64_t analysis_generation = 0, frame_time_ns = 0, scratch_generation = 0, max_peaks = 0;
+        uint32_t wanted = 0;                       // bit i: result array i requested
+        int config = -1;
+        uint64_t graph_launches = 0;
+        int calls = 0;
+    } frame_pipe;
+
     // optional per-kernel timing (pvqt_set_profiling): event pairs around every launch
+    bool frame_pipe_enabled = true;     // PVQT_FRAME_PIPE=0: one-frame pipeline calls take the general path
     bool profiling = false;
     struct Timed { cudaEvent_t a, b; int kind; };
     std::vector<Timed> timed;
@@ -1696,6 +1712,121 @@ void release_instant(pvqt *v)
     I = pvqt::Instant{};
 }
 
+void release_frame_pipe(pvqt *v)
+{
+    pvqt::FramePipe &F = v->frame_pipe;
+    if (F.exec) cudaGraphExecDestroy(F.exec);
+    if (F.h_in) cudaFreeHost(F.h_in);
+    if (F.h_res) cudaFreeHost(F.h_res);
+    if (F.d_res) cudaFree(F.d_res);
+    if (F.d_in) cudaFree(F.d_in);
+    if (F.d_db) cudaFree(F.d_db);
+    F = pvqt::FramePipe{};
+}
+
+// One frame through VQT + AnalysisState (see pvqt::FramePipe).  The first call of a shape runs eagerly (it reserves the
+// scratch and the result mirrors: nothing may be allocated under capture), the second is captured, the later ones replay.
+int run_frame_pipeline(pvqt *v, pvqt_analysis *a, const float *x, uint64_t frame_time_ns, const pvqt_analysis_outputs *out,
+                       uint64_t *d2h_bytes)
+{
+    pvqt::FramePipe &F = v->frame_pipe;
+    const size_t n_fft = (size_t)v->params.n_fft, nb = v->kernel.n_buckets;
+    const size_t skip = std::min(v->upload_skip, n_fft), n_in = n_fft - skip;
+    PVQT_CUDA(cudaSetDevice(v->device));
+    pvqt_analysis_outputs host = *out;
+    uint32_t wanted = 0;
+    size_t res_bytes = 0, off[pvqt_detail::kAnalysisOutputs] = {};
+    for (int i = 0; i < pvqt_detail::kAnalysisOutputs; ++i) {
+        if (!pvqt_detail::analysis_output_member(host, i)) continue;
+        wanted |= 1u << i;
+        off[i] = res_bytes;
+        res_bytes += (pvqt_detail::analysis_output_bytes_per_frame(a, i, out->max_peaks) + 15) & ~(size_t)15;
+    }
+    if (!F.h_in) {
+        PVQT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&F.h_in), std::max<size_t>(n_in, 1) * sizeof(float), cudaHostAllocDefault));
+        PVQT_CUDA(cudaMalloc(reinterpret_cast<void **>(&F.d_in), n_fft * sizeof(float)));
+        PVQT_CUDA(cudaMalloc(reinterpret_cast<void **>(&F.d_db), nb * sizeof(float)));
+        PVQT_CUDA(cudaMemset(F.d_in, 0, n_fft * sizeof(float)));
+    }
+    if (res_bytes > F.h_res_bytes) {
+        if (F.exec) { cudaGraphExecDestroy(F.exec); F.exec = nullptr; F.calls = 0; }
+        if (F.h_res) cudaFreeHost(F.h_res);
+        if (F.d_res) cudaFree(F.d_res);
+        F.h_res = F.d_res = nullptr;
+        F.h_res_bytes = 0;
+        PVQT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&F.h_res), res_bytes, cudaHostAllocDefault));
+        PVQT_CUDA(cudaMalloc(reinterpret_cast<void **>(&F.d_res), res_bytes));
+        F.h_res_bytes = res_bytes;
+    }
+    std::memcpy(F.h_in, x + skip, n_in * sizeof(float));
+    auto enqueue = [&]() -> int {
+        PVQT_CUDA(cudaMemcpyAsync(F.d_in + skip, F.h_in, n_in * sizeof(float), cudaMemcpyHostToDevice, v->stream));
+        int rc = run_device(v, F.d_in, 1, 0, n_fft, 1, F.d_db, nullptr, nullptr, v->stream, 0);
+        if (rc) return rc;
+        // K-analysis writes the frame's results into one device buffer laid out like the pinned one: one clear (slots past
+        // a frame's peak count stay 0, as in the batch calls), one copy back
+        pvqt_analysis_outputs dev{};
+        dev.max_peaks = out->max_peaks;
+        for (int i = 0; i < pvqt_detail::kAnalysisOutputs; ++i)
+            if (wanted >> i & 1u) pvqt_detail::analysis_output_member(dev, i) = F.d_res + off[i];
+        PVQT_CUDA(cudaMemsetAsync(F.d_res, 0, res_bytes, v->stream));
+        rc = pvqt_detail::analysis_run_device(a, F.d_db, 0, 1, 1, frame_time_ns, &dev, 0, v->stream);
+        if (rc) return rc;
+        v->launches.fetch_add(1);
+        PVQT_CUDA(cudaMemcpyAsync(F.h_res, F.d_res, res_bytes, cudaMemcpyDeviceToHost, v->stream));
+        return PVQT_OK;
+    };
+    const int config = (v->fused_ok ? 1 : 0) | (v->cluster_ok ? 2 : 0) | (v->pipe_ok ? 4 : 0);
+    const bool same = F.analysis == a && F.analysis_generation == pvqt_detail::analysis_generation(a) &&
+                      F.frame_time_ns == frame_time_ns && F.wanted == wanted && F.max_peaks == out->max_peaks &&
+                      F.scratch_generation == v->lane[0].spec.generation && F.config == config;
+    if (!same) {
+        if (F.exec) { cudaGraphExecDestroy(F.exec); F.exec = nullptr; }
+        F.calls = 0;
+    }
+    if (!F.exec && F.calls >= 1 && !v->profiling) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = v->launches.load();
+        PVQT_CUDA(cudaStreamBeginCapture(v->stream, cudaStreamCaptureModeThreadLocal));
+        v->capturing = true;
+        int rc = enqueue();
+        v->capturing = false;
+        F.graph_launches = v->launches.load() - before;
+        v->launches.store(before);
+        cudaError_t e = cudaStreamEndCapture(v->stream, &graph);
+        if (rc == PVQT_OK && e == cudaSuccess && graph) {
+            e = cudaGraphInstantiate(&F.exec, graph, 0);
+            if (e != cudaSuccess) F.exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != PVQT_OK) { cudaGetLastError(); return rc; }
+        if (!F.exec) cudaGetLastError();   // capture unsupported here: stay eager
+    }
+    if (F.exec && !v->profiling) {
+        PVQT_CUDA(cudaGraphLaunch(F.exec, v->stream));
+        v->launches.fetch_add(F.graph_launches);
+    } else {
+        int rc = enqueue();
+        if (rc) return rc;
+    }
+    // (the keys are taken after the eager call: it may have grown the scratch or the mirrors)
+    F.analysis = a;
+    F.analysis_generation = pvqt_detail::analysis_generation(a);
+    F.frame_time_ns = frame_time_ns;
+    F.wanted = wanted;
+    F.max_peaks = out->max_peaks;
+    F.scratch_generation = v->lane[0].spec.generation;
+    F.config = config;
+    ++F.calls;
+    PVQT_CUDA(cudaStreamSynchronize(v->stream));
+    for (int i = 0; i < pvqt_detail::kAnalysisOutputs; ++i)
+        if (wanted >> i & 1u)
+            std::memcpy(pvqt_detail::analysis_output_member(host, i), F.h_res + off[i],
+                        pvqt_detail::analysis_output_bytes_per_frame(a, i, out->max_peaks));
+    if (d2h_bytes) *d2h_bytes = res_bytes;
+    return PVQT_OK;
+}
+
 int run_instant(pvqt *v, const float *x, float *out)
 {
     pvqt::Instant &I = v->instant;
@@ -1955,6 +2086,7 @@ int pvqt_create(const pvqt_params *params, int device, pvqt **out, pvqt_error *e
             return cuda_error(e, "allocate K-sdft completion counter");
     }
     if (const char *s = std::getenv("PVQT_TILE_FLAGS")) v->tile_flags = std::atoi(s) != 0;
+    if (const char *s = std::getenv("PVQT_FRAME_PIPE")) v->frame_pipe_enabled = std::atoi(s) != 0;
     if ((e = cudaEventCreateWithFlags(&v->lane_fork, cudaEventDisableTiming)) != cudaSuccess)
         return cuda_error(e, "create launch lanes");
     if (const char *s = std::getenv("PVQT_LANES")) v->n_lanes = std::max(1, std::min(std::atoi(s), (int)pvqt::kLanes));
@@ -2005,6 +2137,7 @@ void pvqt_destroy(pvqt *v)
     }
     if (v->lane_fork) cudaEventDestroy(v->lane_fork);
     release_instant(v);
+    release_frame_pipe(v);
     v->d_audio.release();
     v->d_out.release();
     delete v;
@@ -2124,6 +2257,8 @@ int pvqt_calc_streams_analysis(pvqt *v, pvqt_analysis *a, const float *audio, si
         return fail(PVQT_BAD_LENGTH, "each stream must hold (frames_per_stream - 1) * hop + n_fft samples");
     size_t frames = 0;
     if (!mul_ok(n_streams, frames_per_stream, &frames)) return fail(PVQT_INVALID_ARGUMENT, "too many frames");
+    if (n_streams == 1 && frames_per_stream == 1 && out && !out_db && v->frame_pipe_enabled)
+        return run_frame_pipeline(v, a, audio, frame_time_ns, out, d2h_bytes);
     PVQT_CUDA(cudaSetDevice(v->device));
     pvqt_analysis_outputs dev{};
     int rc = pvqt_detail::analysis_outputs_reserve(a, out, frames, &dev, v->stream);

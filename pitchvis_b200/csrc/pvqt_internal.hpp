@@ -23,4 +23,11 @@ int analysis_outputs_reserve(pvqt_analysis *a, const pvqt_analysis_outputs *host
 int analysis_outputs_download(pvqt_analysis *a, const pvqt_analysis_outputs *host, const pvqt_analysis_outputs *dev,
                               size_t frames, cudaStream_t stream, size_t *bytes);
 
+// The result arrays of pvqt_analysis_outputs by index (declaration order): the member, and its bytes per frame.
+constexpr int kAnalysisOutputs = 11;
+void *&analysis_output_member(pvqt_analysis_outputs &o, int i);
+size_t analysis_output_bytes_per_frame(const pvqt_analysis *a, int i, size_t max_peaks);
+// Changes whenever something a captured launch of K-analysis has baked in does: the parameters, the result mirrors.
+uint64_t analysis_generation(const pvqt_analysis *a);
+
 }  // namespace pvqt_detail

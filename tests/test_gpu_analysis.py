@@ -294,3 +294,32 @@ def test_small_cta_form_gives_the_same_results(vqt, monkeypatch):
     small.close()
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k
+
+
+def test_frame_by_frame_pipeline_matches_the_batch(vqt):
+    # the viewer's loop: one frame of audio per call through VQT + AnalysisState (captured graph after the second call)
+    # against the same recording in one batch call; then a changed smoothing duration must reach the captured launch
+    audio = synth.polyphonic_chords(3.0, 22050.0, seed=5)
+    n_fft = 32768
+    T = 60
+    vqt.set_sliding_dft(0)   # one frame per call transforms every window group with the FFT: the batch must too for equal bits
+    try:
+        batch = pv.AnalysisState(pv.VqtRange())
+        ref = batch.calculate_and_preprocess(vqt, audio[:(T - 1) * HOP + n_fft], HOP, FRAME_NS, max_peaks=48)
+        live = pv.AnalysisState(pv.VqtRange())
+        for t in range(T):
+            r = live.calculate_and_preprocess(vqt, audio[t * HOP:t * HOP + n_fft], HOP, FRAME_NS, frames_per_stream=1, max_peaks=48)
+            for k in ("peak_count", "peak_indices", "peaks_continuous", "smoothed_scene_calmness", "smoothed_tuning_grid_inaccuracy"):
+                assert np.array_equal(r[k][0, 0], ref[k][0, t]), (k, t)
+        batch.update_vqt_smoothing_duration(20 * 1_000_000)
+        live.update_vqt_smoothing_duration(20 * 1_000_000)
+        ref2 = batch.calculate_and_preprocess(vqt, audio[T * HOP:(T + 9) * HOP + n_fft], HOP, FRAME_NS, max_peaks=48)
+        for t in range(10):
+            r = live.calculate_and_preprocess(vqt, audio[(T + t) * HOP:(T + t) * HOP + n_fft], HOP, FRAME_NS, frames_per_stream=1,
+                                              max_peaks=48)
+            for k in ("peak_count", "peak_indices", "smoothed_scene_calmness"):
+                assert np.array_equal(r[k][0, 0], ref2[k][0, t]), (k, t)
+    finally:
+        vqt.set_sliding_dft(2)
+    batch.close()
+    live.close()
