@@ -49,6 +49,9 @@ struct AnalysisKernelParams {
     int32_t  octaves, bpo, nb;
     int32_t  has_horizon;        // x_vqt_smoothed time horizon is Some(..)
     float   *st_smoothed, *st_calm, *st_released, *st_afterglow, *st_scalar;  // per-stream state
+    uint64_t *st_ema_ms;         // per stream and bin: the millisecond horizon st_ema_alpha was evaluated for (~0: none)
+    float   *st_ema_alpha;
+    const float *logf_table;     // ln of every bin's centre frequency (computed once per handle)
     const float *db;             // [S][T][NB]
     uint32_t n_frames;
     uint64_t frame_time_ns;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) analysis_kernel(const __gri
         aglow[b] = P.st_afterglow[so + b];
     }
     // ln of every bin's centre frequency (peak_detection.rs:79-85 evaluates it per peak and frame; it depends on the bin only)
-    for (int b = tid; b < n; b += kThreads) logf_bin[b] = cr_logf(P.min_freq * cr_powf(2.0f, (float)b / (float)P.bpo));
+    for (int b = tid; b < n; b += kThreads) logf_bin[b] = P.logf_table[b];
     if (tid == 0) { s_scene = P.st_scalar[2 * stream]; s_tuning = P.st_scalar[2 * stream + 1]; }
     __syncthreads();
 
@@ -300,7 +303,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) analysis_kernel(const __gri
     uint64_t ema_ms[kBinsPerThread];
     float ema_a[kBinsPerThread];
 #pragma unroll
-    for (int k = 0; k < kBinsPerThread; ++k) { ema_ms[k] = ~0ull; ema_a[k] = 0.0f; }
+    for (int k = 0; k < kBinsPerThread; ++k) {   // the cache outlives the launch (one frame per call: 588 f64 exps per call otherwise)
+        const int b = tid + k * kThreads;
+        ema_ms[k] = b < n ? P.st_ema_ms[so + b] : ~0ull;
+        ema_a[k] = b < n ? P.st_ema_alpha[so + b] : 0.0f;
+    }
     const bool ema_cached = n <= kBinsPerThread * kThreads;
     float base_fm[kBinsPerThread];   // base horizon x the bin's frequency multiplier (analysis.rs:309-318), frame-independent
 #pragma unroll
@@ -610,6 +617,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) analysis_kernel(const __gri
         P.st_afterglow[so + b] = aglow[b];
     }
     if (tid == 0) { P.st_scalar[2 * stream] = s_scene; P.st_scalar[2 * stream + 1] = s_tuning; }
+#pragma unroll
+    for (int k = 0; k < kBinsPerThread; ++k) {
+        const int b = tid + k * kThreads;
+        if (b < n) { P.st_ema_ms[so + b] = ema_ms[k]; P.st_ema_alpha[so + b] = ema_a[k]; }
+    }
+}
+
+// ln(min_freq * 2^(b / bpo)) for every bin, with the kernel's own correctly rounded functions (peak_detection.rs:79-85)
+__global__ void analysis_tables_kernel(float min_freq, int bpo, int nb, float *logf_table)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) logf_table[b] = cr_logf(min_freq * cr_powf(2.0f, (float)b / (float)bpo));
 }
 
 size_t analysis_smem_bytes(int nb)
@@ -628,6 +647,9 @@ struct pvqt_analysis {
     int has_horizon = 1;
     cudaStream_t stream = nullptr;
     float *st_smoothed = nullptr, *st_calm = nullptr, *st_released = nullptr, *st_afterglow = nullptr, *st_scalar = nullptr;
+    uint64_t *st_ema_ms = nullptr;      // alpha cache of the spectrum's EMA, valid for frame time `ema_frame_time_ns`
+    float *st_ema_alpha = nullptr, *logf_table = nullptr;
+    uint64_t ema_frame_time_ns = 0;
     // device mirrors of the result buffers of the single-call pipeline (pvqt_calc_*_analysis), reused across calls
     static constexpr int kOutputs = 11;
     void *mirror[kOutputs] = {};
@@ -722,6 +744,15 @@ int pvqt_analysis_create(const pvqt_range *range, const pvqt_analysis_params *pa
     }
     ACUDA(cudaMalloc(&a->st_scalar, n_streams * 2 * sizeof(float)));
     ACUDA(cudaMemset(a->st_scalar, 0, n_streams * 2 * sizeof(float)));
+    ACUDA(cudaMalloc(&a->st_ema_ms, n_streams * nb * sizeof(uint64_t)));
+    ACUDA(cudaMemset(a->st_ema_ms, 0xff, n_streams * nb * sizeof(uint64_t)));
+    ACUDA(cudaMalloc(&a->st_ema_alpha, bytes));
+    ACUDA(cudaMemset(a->st_ema_alpha, 0, bytes));
+    ACUDA(cudaMalloc(&a->logf_table, nb * sizeof(float)));
+    analysis_tables_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, a->stream>>>(range->min_freq, (int)range->buckets_per_octave, (int)nb,
+                                                                              a->logf_table);
+    ACUDA(cudaGetLastError());
+    ACUDA(cudaStreamSynchronize(a->stream));
     for (auto k : {(const void *)analysis_kernel<kThreads, 1>, (const void *)analysis_kernel<kThreads, 2>,
                    (const void *)analysis_kernel<kSmallThreads, 5>})
         ACUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)analysis_smem_bytes((int)nb)));
@@ -735,6 +766,9 @@ void pvqt_analysis_destroy(pvqt_analysis *a)
     cudaSetDevice(a->device);
     if (a->stream) { cudaStreamSynchronize(a->stream); cudaStreamDestroy(a->stream); }
     for (float *p : {a->st_smoothed, a->st_calm, a->st_released, a->st_afterglow, a->st_scalar}) cudaFree(p);
+    cudaFree(a->st_ema_ms);
+    cudaFree(a->st_ema_alpha);
+    cudaFree(a->logf_table);
     for (void *p : a->mirror) if (p) cudaFree(p);
     delete a;
 }
@@ -789,6 +823,14 @@ int pvqt_detail::analysis_run_device(pvqt_analysis *a, const float *d_db, size_t
     const size_t so = first_stream * a->nb;
     P.st_smoothed = a->st_smoothed + so; P.st_calm = a->st_calm + so; P.st_released = a->st_released + so;
     P.st_afterglow = a->st_afterglow + so; P.st_scalar = a->st_scalar + 2 * first_stream;
+    // alpha depends on the frame time too: another frame time invalidates the whole cache (every stream's)
+    if (a->ema_frame_time_ns != frame_time_ns) {
+        ACUDA(cudaMemsetAsync(a->st_ema_ms, 0xff, a->n_streams * a->nb * sizeof(uint64_t), st));
+        a->ema_frame_time_ns = frame_time_ns;
+    }
+    P.st_ema_ms = a->st_ema_ms + so;
+    P.st_ema_alpha = a->st_ema_alpha + so;
+    P.logf_table = a->logf_table;
     P.db = d_db;
     P.n_frames = (uint32_t)n_frames;
     P.frame_time_ns = frame_time_ns;
