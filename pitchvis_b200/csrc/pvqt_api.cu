@@ -1769,11 +1769,11 @@ int run_frame_pipeline(pvqt *v, pvqt_analysis *a, const float *x, uint64_t frame
         dev.max_peaks = out->max_peaks;
         for (int i = 0; i < pvqt_detail::kAnalysisOutputs; ++i)
             if (wanted >> i & 1u) pvqt_detail::analysis_output_member(dev, i) = F.d_res + off[i];
-        PVQT_CUDA(cudaMemsetAsync(F.d_res, 0, res_bytes, v->stream));
+        if (res_bytes) PVQT_CUDA(cudaMemsetAsync(F.d_res, 0, res_bytes, v->stream));
         rc = pvqt_detail::analysis_run_device(a, F.d_db, 0, 1, 1, frame_time_ns, &dev, 0, v->stream);
         if (rc) return rc;
         v->launches.fetch_add(1);
-        PVQT_CUDA(cudaMemcpyAsync(F.h_res, F.d_res, res_bytes, cudaMemcpyDeviceToHost, v->stream));
+        if (res_bytes) PVQT_CUDA(cudaMemcpyAsync(F.h_res, F.d_res, res_bytes, cudaMemcpyDeviceToHost, v->stream));
         return PVQT_OK;
     };
     const int config = (v->fused_ok ? 1 : 0) | (v->cluster_ok ? 2 : 0) | (v->pipe_ok ? 4 : 0);

@@ -323,3 +323,30 @@ def test_frame_by_frame_pipeline_matches_the_batch(vqt):
         vqt.set_sliding_dft(2)
     batch.close()
     live.close()
+
+
+def test_frame_pipeline_with_no_results_requested(vqt):
+    # one frame per call with an outputs struct that names no array: the states advance, nothing is copied
+    import ctypes as C
+    from pitchvis_b200 import _ffi
+    lib = _ffi.load()
+    audio = synth.polyphonic_chords(2.0, 22050.0, seed=1)
+    a = pv.AnalysisState(pv.VqtRange())
+    outs = _ffi.PvqtAnalysisOutputs()
+    outs.max_peaks = 8
+    moved = C.c_uint64(123)
+    for t in range(3):
+        x = np.ascontiguousarray(audio[t * HOP:t * HOP + 32768])
+        rc = lib.pvqt_calc_batch_analysis(vqt.handle, a._h, x.ctypes.data_as(C.POINTER(C.c_float)), 32768, HOP, 1, FRAME_NS,
+                                          C.byref(outs), None, C.byref(moved))
+        assert rc == 0 and moved.value == 0
+    # the state did advance: the next frame's results equal those of a state that saw the same four frames with results
+    b = pv.AnalysisState(pv.VqtRange())
+    for t in range(3):
+        b.calculate_and_preprocess(vqt, audio[t * HOP:t * HOP + 32768], HOP, FRAME_NS, frames_per_stream=1, max_peaks=32)
+    ra = a.calculate_and_preprocess(vqt, audio[3 * HOP:3 * HOP + 32768], HOP, FRAME_NS, frames_per_stream=1, max_peaks=32)
+    rb = b.calculate_and_preprocess(vqt, audio[3 * HOP:3 * HOP + 32768], HOP, FRAME_NS, frames_per_stream=1, max_peaks=32)
+    for k in ("peak_count", "peak_indices", "smoothed_scene_calmness"):
+        assert np.array_equal(ra[k], rb[k]), k
+    a.close()
+    b.close()
